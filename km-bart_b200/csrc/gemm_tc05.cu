@@ -1,0 +1,633 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  D[M,N] = epilogue(sum_k A(m,k) * B(n,k)).
+//
+// One persistent CTA per SM, 256 threads, warp-specialised:
+//   warp 0      TMA producer   (one elected lane; cp.async.bulk.tensor 2D, SWIZZLE_128B)
+//   warp 1      MMA issuer     (one elected lane; tcgen05.mma cta_group::1, M=128, N=BN, K=16|8)
+//   warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns)
+//   warps 4..7  epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+// Three mbarrier pipelines: smem full/empty (TMA<->MMA), tmem full/empty (MMA<->epilogue),
+// and a static round-robin tile schedule.  Operands may be K-major or MN-major (the
+// backward GEMMs contract over the token dimension, which is the slow dimension of
+// every activation), bf16 or tf32.
+//
+// Replaces the cuBLAS calls the reference issues through nn.Linear / F.linear
+// (SURVEY.md §2.3(b) K2,K5,K7,K8,K10) — see include/kmbart.h for the call-site map.
+#include <cuda.h>
+#include <stdio.h>
+#include <mutex>
+#include "common.cuh"
+#include "../../include/kmbart.h"
+
+namespace kmb {
+
+constexpr int BM = 128;
+constexpr int TILE_BYTES_ROW = 128;  // one swizzle span: 64 bf16 or 32 tf32
+constexpr int A_TILE_BYTES = BM * TILE_BYTES_ROW;
+
+struct GemmParams {
+  int M, N, K;
+  int m_tiles, n_tiles, k_blocks;
+  KmbGemmEpilogue e;
+  int vec_ok;  // all leading dims / pointers allow 16-byte row-segment access
+  uint32_t drop_thresh16;
+  float drop_scale;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = BN * TILE_BYTES_ROW;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGES_RAW = (227 * 1024 - 2048) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// Instruction descriptor, field layout per cute/arch/mma_sm100_desc.hpp InstrDescriptor.
+__device__ __forceinline__ uint32_t make_idesc(int elt, int a_mn, int b_mn, int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;                             // c_format = F32
+  const uint32_t fmt = elt == 0 ? 1u : 2u;  // BF16 : TF32
+  d |= fmt << 7;                            // a_format
+  d |= fmt << 10;                           // b_format
+  d |= (uint32_t)a_mn << 15;                // a_major (0 = K, 1 = MN)
+  d |= (uint32_t)b_mn << 16;                // b_major
+  d |= (uint32_t)(n >> 3) << 17;            // n_dim
+  d |= (uint32_t)(BM >> 4) << 24;           // m_dim
+  return d;
+}
+
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// ------------------------------------------------------------------ epilogue: 32 columns of one row
+template <int BN>
+__device__ __forceinline__ void epilogue_linear(const GemmParams& p, float (&v)[32], int row,
+                                                int col0, int ncols /*valid cols in chunk*/,
+                                                uint64_t seed) {
+  const KmbGemmEpilogue& e = p.e;
+  const bool full = (ncols == 32) && p.vec_ok;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
+  if (e.bias) {
+    if (full) {
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 t = __ldg(b4 + j);
+        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) v[j] += __ldg(e.bias + col0 + j);
+    }
+  }
+  if (e.act == KMB_ACT_GELU) {
+    if (e.out_preact) {
+      bf16* pp = reinterpret_cast<bf16*>(e.out_preact) + (int64_t)row * e.ld_bf16 + col0;
+      if (full) {
+        uint4* q = reinterpret_cast<uint4*>(pp);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          q[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) pp[j] = __float2bfloat16(v[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (e.act == KMB_ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+  } else if (e.act == KMB_ACT_GELU_GRAD || e.act == KMB_ACT_TANH_GRAD) {
+    const bf16* ap = reinterpret_cast<const bf16*>(e.aux) + (int64_t)row * e.ld_aux + col0;
+    float a[32];
+    if (full) {
+      const uint4* q = reinterpret_cast<const uint4*>(ap);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 t = __ldg(q + j);
+        a[8 * j] = bf16lo(t.x); a[8 * j + 1] = bf16hi(t.x);
+        a[8 * j + 2] = bf16lo(t.y); a[8 * j + 3] = bf16hi(t.y);
+        a[8 * j + 4] = bf16lo(t.z); a[8 * j + 5] = bf16hi(t.z);
+        a[8 * j + 6] = bf16lo(t.w); a[8 * j + 7] = bf16hi(t.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] = (j < ncols) ? __bfloat162float(ap[j]) : 0.f;
+    }
+    if (e.act == KMB_ACT_GELU_GRAD) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(a[j]);
+    } else {  // aux holds tanh output y: d/dx = 1 - y^2
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= (1.f - a[j] * a[j]);
+    }
+  }
+  if (p.drop_thresh16) {
+    const uint64_t base = (uint64_t)row * (uint64_t)p.N + (uint64_t)col0;  // col0 % 32 == 0
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint64_t bits = dropout_bits4(seed, e.dropout_tag, (base >> 2) + j);
+#pragma unroll
+      for (int l = 0; l < 4; ++l)
+        v[4 * j + l] = dropout_keep(bits, l, p.drop_thresh16) ? v[4 * j + l] * p.drop_scale : 0.f;
+    }
+  }
+  if (e.residual) {
+    const float* rp = e.residual + (int64_t)row * e.ld_res + col0;
+    if (full) {
+      const float4* r4 = reinterpret_cast<const float4*>(rp);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 t = __ldg(r4 + j);
+        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) v[j] += rp[j];
+    }
+  }
+  if (e.out_f32) {
+    float* op = e.out_f32 + (int64_t)row * e.ld_f32 + col0;
+    if (full) {
+      float4* o4 = reinterpret_cast<float4*>(op);
+      if (e.accumulate) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 t = o4[j];
+          v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) {
+          if (e.accumulate) v[j] += op[j];
+          op[j] = v[j];
+        }
+    }
+  }
+  if (e.out_bf16) {
+    bf16* op = reinterpret_cast<bf16*>(e.out_bf16) + (int64_t)row * e.ld_bf16 + col0;
+    if (full) {
+      uint4* q = reinterpret_cast<uint4*>(op);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        q[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                          pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) op[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+template <int BN, int ELT, int A_MN, int B_MN>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int ELT_BYTES = ELT == 0 ? 2 : 4;
+  constexpr int BK = TILE_BYTES_ROW / ELT_BYTES;  // 64 bf16 / 32 tf32 per k-block
+  constexpr int UK = 32 / ELT_BYTES;              // UMMA K: 16 bf16 / 8 tf32
+  constexpr int KSTEPS = BK / UK;                 // 4
+  constexpr int MN_CHUNK = BK;                    // elements per 128-byte row of an MN-major tile
+  static_assert(!B_MN || BN >= MN_CHUNK, "MN-major B needs BN >= one 128-byte chunk");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = (t % p.m_tiles) * BM;
+        const int n0 = (t / p.m_tiles) * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (A_MN == 0) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / MN_CHUNK; ++c)
+              tma_load_2d(sa + c * BK * TILE_BYTES_ROW, &tmA, &full_bar[stage], m0 + c * MN_CHUNK, k0);
+          }
+          if (B_MN == 0) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / MN_CHUNK; ++c)
+              tma_load_2d(sb + c * BK * TILE_BYTES_ROW, &tmB, &full_bar[stage], n0 + c * MN_CHUNK, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(ELT, A_MN, B_MN, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS; ++kk) {
+            uint64_t da, db;
+            if (A_MN == 0) da = make_smem_desc_sw128(sa + kk * 32, 16, 1024);
+            else da = make_smem_desc_sw128(sa + kk * UK * TILE_BYTES_ROW, BK * TILE_BYTES_ROW, 1024);
+            if (B_MN == 0) db = make_smem_desc_sw128(sb + kk * 32, 16, 1024);
+            else db = make_smem_desc_sw128(sb + kk * UK * TILE_BYTES_ROW, BK * TILE_BYTES_ROW, 1024);
+            if (ELT == 0) umma_f16(tmem_d, da, db, idesc, (kb | kk) != 0);
+            else umma_tf32(tmem_d, da, db, idesc, (kb | kk) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint64_t seed = (p.drop_thresh16 && p.e.dropout_seed) ? *p.e.dropout_seed : 0ull;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
+      const int row = m_blk * BM + q * 32 + lane;
+      const int n0 = n_blk * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      const bool row_ok = row < p.M;
+
+      if (p.e.mode == KMB_EPI_LINEAR) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          int ncols = p.N - col0;
+          ncols = ncols > 32 ? 32 : ncols;
+          if (row_ok && ncols > 0) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            epilogue_linear<BN>(p, v, row, col0, ncols, seed);
+          }
+        }
+      } else if (p.e.mode == KMB_EPI_CE_STATS) {
+        // online softmax partial over this tile's columns (+ final_logits_bias)
+        float mx = -INFINITY, sm = 0.f;
+        const int64_t label = row_ok ? p.e.labels[row] : -100;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          int ncols = p.N - col0;
+          ncols = ncols > 32 ? 32 : ncols;
+          if (row_ok && ncols > 0) {
+            float v[32];
+            float cm = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = __uint_as_float(r[j]) * p.e.alpha;
+              if (j < ncols) {
+                if (p.e.bias) v[j] += __ldg(p.e.bias + col0 + j);
+                cm = fmaxf(cm, v[j]);
+              }
+            }
+            const float nm = fmaxf(mx, cm);
+            float cs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) cs += __expf(v[j] - nm);
+            sm = sm * __expf(mx - nm) + cs;
+            mx = nm;
+            if (label >= col0 && label < col0 + ncols) {
+              float lv = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j == (int)label) lv = v[j];
+              p.e.ce_label_logit[row] = lv;
+            }
+          }
+        }
+        if (row_ok) {
+          p.e.ce_max[(int64_t)row * p.n_tiles + n_blk] = mx;
+          p.e.ce_sum[(int64_t)row * p.n_tiles + n_blk] = sm;
+        }
+      } else {  // KMB_EPI_CE_GRAD
+        const int64_t label = row_ok ? p.e.labels[row] : -100;
+        const float lse = row_ok ? p.e.ce_lse[row] : 0.f;
+        const float gs = (label >= 0) ? *p.e.ce_gscale : 0.f;
+        bf16* orow = reinterpret_cast<bf16*>(p.e.out_bf16) + (int64_t)row * p.e.ld_bf16;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          int ncols = p.N - col0;
+          ncols = ncols > 32 ? 32 : ncols;
+          if (row_ok && ncols > 0) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(r[j]) * p.e.alpha;
+              if (p.e.bias && j < ncols) x += __ldg(p.e.bias + col0 + j);
+              float pr = __expf(x - lse);
+              if (col0 + j == (int)label) pr -= 1.f;
+              v[j] = pr * gs;
+            }
+            if (ncols == 32 && p.vec_ok) {
+              uint4* qd = reinterpret_cast<uint4*>(orow + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                qd[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) orow[col0 + j] = __float2bfloat16(v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+// 2-D map over a row-major [rows, ld] matrix with `cols` valid columns, box = (box_cols, box_rows)
+static int make_tmap(CUtensorMap* tm, const void* ptr, int elt, uint64_t rows, uint64_t cols,
+                     uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    kmb_set_last_error("cuTensorMapEncodeTiled entry point unavailable", __FILE__, __LINE__);
+    return KMB_ERR_TMAP;
+  }
+  const uint64_t esz = elt == 0 ? 2 : 4;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * esz};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, elt == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu box=%ux%u",
+             (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_cols, box_rows);
+    kmb_set_last_error(msg, __FILE__, __LINE__);
+    return KMB_ERR_TMAP;
+  }
+  return KMB_OK;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, int ELT, int A_MN, int B_MN>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+  using C = Cfg<BN>;
+  auto kern = gemm_tc05_kernel<BN, ELT, A_MN, B_MN>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      kmb_set_last_error(cudaGetErrorString(e), __FILE__, __LINE__);
+      return KMB_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, 256, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+  KMB_CHECK_LAUNCH();
+  return KMB_OK;
+}
+
+template <int BN, int ELT>
+static int launch_major(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                        const GemmParams& p, cudaStream_t st) {
+  // an MN-major B tile is built from 128-byte-wide chunks, so BN must cover one chunk
+  constexpr bool kBmnOk = BN >= (ELT == 0 ? 64 : 32);
+  if (!a_mn && !b_mn) return launch<BN, ELT, 0, 0>(tmA, tmB, p, st);
+  if (a_mn && !b_mn) return launch<BN, ELT, 1, 0>(tmA, tmB, p, st);
+  if constexpr (kBmnOk) {
+    if (!a_mn && b_mn) return launch<BN, ELT, 0, 1>(tmA, tmB, p, st);
+    return launch<BN, ELT, 1, 1>(tmA, tmB, p, st);
+  }
+  kmb_set_last_error("kmb_gemm: tile_n too narrow for an MN-major B operand", __FILE__, __LINE__);
+  return KMB_ERR_ARG;
+}
+
+}  // namespace kmb
+
+extern "C" int kmb_gemm_pick_tile_n(int M, int N) {
+  // Largest tile whose tile count still fills the 148 SMs reasonably; small-M (decode)
+  // problems get narrow tiles so that many CTAs stream the weights concurrently.
+  const int mt = (M + kmb::BM - 1) / kmb::BM;
+  const int cands[4] = {256, 128, 64, 32};
+  int best = 32;
+  double best_score = -1.0;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    if (bn > 32 && bn / 2 >= N) continue;  // do not pad N by more than 2x
+    const int tiles = mt * ((N + bn - 1) / bn);
+    const int waves = (tiles + 147) / 148;
+    const double eff = (double)tiles / (waves * 148.0);           // SM fill
+    const double npad = (double)N / (((N + bn - 1) / bn) * bn);   // useful columns
+    const double shape = bn >= 128 ? 1.0 : (bn == 64 ? 0.8 : 0.6);  // MMA efficiency of narrow tiles
+    const double score = eff * npad * shape;
+    if (score > best_score + 1e-9) { best_score = score; best = bn; }
+  }
+  return best;
+}
+
+extern "C" int kmb_gemm_n_tiles(int N, int tile_n) {
+  if (tile_n != 32 && tile_n != 64 && tile_n != 128 && tile_n != 256) return KMB_ERR_ARG;
+  return (N + tile_n - 1) / tile_n;
+}
+
+extern "C" int kmb_gemm(const void* A, const void* B, int M, int N, int K, int64_t lda, int64_t ldb,
+                        int a_mn, int b_mn, int elt, const KmbGemmEpilogue* epi, int tile_n,
+                        kmb_stream_t stream) {
+  using namespace kmb;
+  if (!A || !B || !epi || M <= 0 || N <= 0 || K <= 0 || (elt != 0 && elt != 1)) {
+    kmb_set_last_error("kmb_gemm: bad argument", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  const int esz = elt == 0 ? 2 : 4;
+  if ((lda * esz) % 16 || (ldb * esz) % 16 || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) {
+    kmb_set_last_error("kmb_gemm: operands must be 16-byte aligned with 16-byte row pitch", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  if (tile_n == 0) tile_n = kmb_gemm_pick_tile_n(M, N);
+  if (tile_n != 32 && tile_n != 64 && tile_n != 128 && tile_n != 256) {
+    kmb_set_last_error("kmb_gemm: tile_n must be 32/64/128/256", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  const int bk = TILE_BYTES_ROW / esz;
+  if (b_mn && tile_n < bk) tile_n = bk;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = (N + tile_n - 1) / tile_n;
+  p.k_blocks = (K + bk - 1) / bk;
+  p.e = *epi;
+  p.drop_thresh16 = 0;
+  p.drop_scale = 1.f;
+  if (epi->dropout_p > 0.f) {
+    if (!epi->dropout_seed) {
+      kmb_set_last_error("kmb_gemm: dropout needs a device seed pointer", __FILE__, __LINE__);
+      return KMB_ERR_ARG;
+    }
+    p.drop_thresh16 = (uint32_t)(epi->dropout_p * 65536.0f + 0.5f);
+    p.drop_scale = 1.0f / (1.0f - epi->dropout_p);
+  }
+  auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+  p.vec_ok = 1;
+  if (epi->bias && !al16(epi->bias)) p.vec_ok = 0;
+  if (epi->residual && (!al16(epi->residual) || (epi->ld_res % 4))) p.vec_ok = 0;
+  if (epi->aux && (!al16(epi->aux) || (epi->ld_aux % 8))) p.vec_ok = 0;
+  if (epi->out_f32 && (!al16(epi->out_f32) || (epi->ld_f32 % 4))) p.vec_ok = 0;
+  if ((epi->out_bf16 || epi->out_preact) && (epi->ld_bf16 % 8)) p.vec_ok = 0;
+  if (epi->out_bf16 && !al16(epi->out_bf16)) p.vec_ok = 0;
+  if (epi->out_preact && !al16(epi->out_preact)) p.vec_ok = 0;
+  if (epi->mode == KMB_EPI_CE_STATS && (!epi->labels || !epi->ce_max || !epi->ce_sum || !epi->ce_label_logit)) {
+    kmb_set_last_error("kmb_gemm: CE_STATS needs labels/ce_max/ce_sum/ce_label_logit", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  if (epi->mode == KMB_EPI_CE_GRAD && (!epi->labels || !epi->ce_lse || !epi->ce_gscale || !epi->out_bf16)) {
+    kmb_set_last_error("kmb_gemm: CE_GRAD needs labels/ce_lse/ce_gscale/out_bf16", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a_mn) rc = make_tmap(&tmA, A, elt, (uint64_t)M, (uint64_t)K, (uint64_t)lda, bk, BM);
+  else rc = make_tmap(&tmA, A, elt, (uint64_t)K, (uint64_t)M, (uint64_t)lda, bk, bk);
+  if (rc) return rc;
+  if (!b_mn) rc = make_tmap(&tmB, B, elt, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, bk, tile_n);
+  else rc = make_tmap(&tmB, B, elt, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, bk, bk);
+  if (rc) return rc;
+
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define KMB_DISPATCH_BN(BNV)                                                        \
+  case BNV:                                                                         \
+    return elt == 0 ? launch_major<BNV, 0>(a_mn, b_mn, tmA, tmB, p, st)             \
+                    : launch_major<BNV, 1>(a_mn, b_mn, tmA, tmB, p, st);
+  switch (tile_n) {
+    KMB_DISPATCH_BN(32)
+    KMB_DISPATCH_BN(64)
+    KMB_DISPATCH_BN(128)
+    KMB_DISPATCH_BN(256)
+  }
+#undef KMB_DISPATCH_BN
+  return KMB_ERR_ARG;
+}
