@@ -100,6 +100,120 @@ int kmb_gemm(const void* A, const void* B, int M, int N, int K, int64_t lda, int
 int kmb_gemm_n_tiles(int N, int tile_n);
 int kmb_gemm_pick_tile_n(int M, int N);
 
+/* ------------------------------------------------------------------------------
+ * Fused multi-head attention, head_dim = 64, bf16 in/out, fp32 online softmax.
+ * replaces: HF-3.0.2 SelfAttention.forward — bmm(q,k^T), additive causal mask
+ *   (src/model/model.py:63-70), key-padding masked_fill (src/model/modules.py:130-131),
+ *   softmax, bmm(p,v) — instantiated at src/model/modules.py:84 and src/model/model.py:35.
+ * q/k/v/o are token-major with element row strides ld*; head h lives in columns
+ * [64h, 64h+64).  key_pad: [B, Sk] bytes, 1 = padding (or NULL).  lse: [B, H, Sq].
+ * `scale` multiplies q.k (dh^-0.5; the reference scales q instead, same product).
+ */
+int kmb_attn_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                 void* o, int64_t ldo, float* lse, const uint8_t* key_pad, int B, int H, int Sq, int Sk,
+                 int head_dim, int causal, float scale, kmb_stream_t stream);
+/* Same kernel with explicit element strides {batch, head, row} for q, k, v, o (12 values), so
+ * the legacy KV-cache layout [B, H, T, 64] of HF-3.0.2 layer_state (prev_key / prev_value,
+ * reordered by src/model/mixins.py:419-434) can be consumed in place. */
+int kmb_attn_fwd_strided(const void* q, const void* k, const void* v, void* o, const int64_t* strides12,
+                         const uint8_t* key_pad, int B, int H, int Sq, int Sk, int head_dim, int causal,
+                         float scale, kmb_stream_t stream);
+/* autograd backward of the above; d_scratch: [B, H, Sq] floats. */
+int kmb_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                 const void* o, int64_t ldo, const void* d_o, int64_t lddo, const float* lse,
+                 float* d_scratch, const uint8_t* key_pad, void* dq, void* dk, void* dv, int64_t lddq,
+                 int64_t lddk, int64_t lddv, int B, int H, int Sq, int Sk, int head_dim, int causal,
+                 float scale, kmb_stream_t stream);
+
+/* ------------------------------------------------------------------------------
+ * Visual-token embedding path.
+ * replaces: ImageEmbedding.forward (src/model/modules.py:24-41: torch.cat of the ragged
+ *   list + Linear(2052->d) + Python split) and _embed_multi_modal (src/model/modules.py:89-102).
+ * kmb_pack_features: list of B fp32 [n_i, 2052] tensors (device pointer table + row offsets
+ *   [B+1]) or one packed [R, 2052] buffer -> bf16 RoI features [R, 2048] + fp32 boxes [R, 4].
+ * kmb_slot_index: slot_idx[b, s] = packed RoI row that overwrites token (b, s), else -1.
+ */
+int kmb_pack_features(const float* const* feat_ptrs, const int* row_offsets, int B, const float* packed,
+                      void* feats_bf16, float* boxes, int R, kmb_stream_t stream);
+int kmb_slot_index(const int64_t* input_ids, const int* row_offsets, int B, int S, int img_feat_id,
+                   int cls_token_id, int* slot_idx, kmb_stream_t stream);
+/* (token gather | visual GEMM row + bias + box projection) * embed_scale + learned position
+ * (offset 2) -> LayerNorm(eps 1e-5) -> dropout.
+ * replaces: src/model/modules.py:93-100, :133-137 (encoder) and HF-3.0.2 BartDecoder.forward
+ *   embed+pos+LN (decoder; pass slot_idx = NULL).  pos_index != NULL: every row uses position
+ *   *pos_index (cached decode, LearnedPositionalEmbedding(use_cache=True)). */
+int kmb_embed_ln_fwd(const int64_t* ids, const int* slot_idx, const float* tok_emb, const float* pos_emb,
+                     const float* vis_acc, const float* boxes, const float* w_box, const float* b_img,
+                     const float* gamma, const float* beta, float* pre, float* out_f32, void* out_bf16,
+                     float* mean, float* rstd, int M, int S, int d, int pos_offset, const int* pos_index,
+                     float embed_scale, float dropout_p, uint32_t dropout_tag, const uint64_t* dropout_seed,
+                     kmb_stream_t stream);
+int kmb_embed_bwd(const float* demb, const int64_t* ids, const int* slot_idx, float* d_tok, void* dvis_bf16,
+                  float* dpos, int B, int S, int d, int pos_offset, int pad_id, float embed_scale,
+                  int accumulate_pos, kmb_stream_t stream);
+int kmb_box_wgrad(const void* dvis_bf16, const float* boxes, float* dw_img, int R, int d, int ld_w,
+                  kmb_stream_t stream);
+
+/* ------------------------------------------------------------------------------
+ * LayerNorm (eps 1e-5) on the fp32 residual stream.
+ * replaces: HF-3.0.2 LayerNorm = torch.nn.LayerNorm in EncoderLayer/DecoderLayer (post-LN,
+ *   normalize_before=False) and layernorm_embedding (src/model/modules.py:85,136).
+ * bwd also produces dz = dropout-re-masked bf16 copy of dpre (the dY operand of the Linear
+ * that fed the residual add) and accumulates dgamma/dbeta/dbias column sums.
+ */
+int kmb_layernorm_fwd(const float* pre, const float* gamma, const float* beta, float* out_f32,
+                      void* out_bf16, float* mean, float* rstd, int M, int d, kmb_stream_t stream);
+int kmb_layernorm_bwd(const float* dy, const float* pre, const float* mean, const float* rstd,
+                      const float* gamma, float* dpre, void* dz_bf16, float* dgamma, float* dbeta,
+                      float* dbias, int M, int d, float drop_in_p, uint32_t drop_in_tag, float drop_out_p,
+                      uint32_t drop_out_tag, const uint64_t* dropout_seed, kmb_stream_t stream);
+int kmb_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, kmb_stream_t stream);
+int kmb_gather_rows_bf16(const void* src, int64_t ld_src, const int* idx, void* out, int64_t ld_out, int n,
+                         int d, kmb_stream_t stream);
+int kmb_scatter_add_rows(const void* src_bf16, int64_t ld_src, const int* idx, float* dst, int64_t ld_dst,
+                         int n, int d, kmb_stream_t stream);
+
+/* ------------------------------------------------------------------------------
+ * Losses.
+ * kmb_ce_combine: reduces the KMB_EPI_CE_STATS partials to per-row log-sum-exp and the mean
+ *   cross-entropy over labels != -100 — nn.CrossEntropyLoss() at src/model/model.py:401-402
+ *   (:299-301 with lm_loss_factor).  acc2 = {sum, count} scratch; loss_total (+)= loss.
+ * kmb_ce_gscale: gscale = upstream * factor / count for the KMB_EPI_CE_GRAD epilogue.
+ * kmb_small_xent: pretraining heads — mode 0 CE mean (src/model/model.py:264-266, :285-287),
+ *   mode 1 KL-div batchmean on log_softmax (src/model/model.py:253-255).
+ */
+int kmb_ce_combine(const float* ce_max, const float* ce_sum, const float* label_logit, const int64_t* labels,
+                   int M, int n_tiles, float* lse, float* row_loss, float* acc2, float factor,
+                   float* loss_out, float* loss_total, int add_total, kmb_stream_t stream);
+int kmb_ce_gscale(const float* acc2, const float* upstream, float factor, float* gscale, kmb_stream_t stream);
+int kmb_small_xent(const float* logits, int64_t ld, int n, int C, int mode, const int64_t* labels,
+                   const float* soft, int64_t ld_soft, float factor, float* loss_accum, void* dlogits_bf16,
+                   int64_t ld_d, const float* upstream, kmb_stream_t stream);
+
+/* ------------------------------------------------------------------------------
+ * Optimizer: one launch over every parameter tensor.
+ * replaces: transformers.AdamW.step (HF-3.0.2 optimization.py; constructed at
+ *   vcg_train.py:100 / pretrain.py:100, stepped at src/training.py:136-143).
+ * table_dev: device array of {float* p; const float* g; float* m; float* v; bf16* p16;
+ * int64 n}; chunk_map_dev: device array of int2 {tensor, chunk}; chunks are
+ * kmb_adamw_chunk_elems() elements.  step_dev is incremented on device (graph-replay
+ * safe).  p16 (optional) receives the refreshed bf16 shadow weights.
+ */
+int kmb_adamw_chunk_elems(void);
+int kmb_adamw_multi(const void* table_dev, const void* chunk_map_dev, int n_chunks, int* step_dev, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int correct_bias,
+                    const float* inv_scale_dev, kmb_stream_t stream);
+int kmb_cast_bf16(const float* src, void* dst, int64_t n, kmb_stream_t stream);
+int kmb_repack_img_weight(const float* w, void* w_feat_bf16, float* w_box, int d, int fin, kmb_stream_t stream);
+/* attention_mask (int64, 1 = keep) -> padding bytes (1 = pad): HF-3.0.2 invert_mask
+ * (src/model/modules.py:130-131) */
+int kmb_invert_mask(const int64_t* mask, uint8_t* pad, int64_t n, kmb_stream_t stream);
+/* advances the device-resident dropout seed stream (no host RNG in the step, graph-replay safe) */
+int kmb_next_seed(uint64_t* state, uint64_t* out, kmb_stream_t stream);
+/* fp32 [rows, K] -> 3xTF32 operand [rows, 3K] (side 0: hi|hi|lo, side 1: hi|lo|hi) for the
+ * fp32-parity mode of kmb_gemm(elt = 1) */
+int kmb_split_tf32(const float* src, int64_t ld_src, float* dst, int rows, int K, int side, kmb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

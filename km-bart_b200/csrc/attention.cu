@@ -1,0 +1,453 @@
+// Fused multi-head attention (training / prefill), head_dim 64, bf16 in, fp32 softmax.
+//
+// Replaces HF-3.0.2 SelfAttention.forward as instantiated by the reference
+// (src/model/modules.py:84 encoder self-attention; src/model/model.py:35 decoder self- and
+// cross-attention; masks built at src/model/modules.py:130-131 and src/model/model.py:63-70):
+//   w = (q*dh^-0.5) k^T ; w += causal ; w.masked_fill(key_padding, -inf) ; softmax ; w v
+// The [B*h, S, S] score tensor of the reference never reaches HBM: scores live in registers
+// (flash-style online softmax over 64-key blocks), only O and the row log-sum-exp are written.
+// S is ~100 / ~48 on this path and attention is 1.7 % of the FLOPs, so the
+// contractions run on mma.sync m16n8k16 (one warp = 16 query rows); the kernel's job is to
+// remove the score round-trips, not to chase tcgen05 utilisation.
+//
+// Backward is two kernels that both recompute the scores: one owns query rows (dQ), the
+// other owns key rows and works on the transposed problem (dK, dV); no atomics.
+#include "common.cuh"
+#include "../../include/kmbart.h"
+
+namespace kmb {
+
+constexpr int TQ = 64;   // rows owned by a CTA (4 warps x 16)
+constexpr int TK = 64;   // streamed block
+constexpr int DH = 64;
+constexpr int LDS = 72;  // padded smem row (elements) -> conflict-free ldmatrix
+
+struct AttnParams {
+  const bf16 *q, *k, *v;
+  int64_t ldq, ldk, ldv;
+  bf16* o;
+  int64_t ldo;
+  // element strides between batches / heads: token-major [B*S, H*64] uses (S*ld, 64),
+  // the legacy cache layout [B, H, S, 64] uses (H*S*64, S*64) with ld = 64
+  int64_t sbq, shq, sbk, shk, sbv, shv, sbo, sho;
+  float* lse;              // [B, H, Sq]
+  const uint8_t* key_pad;  // [B, Sk], 1 = padding, or null
+  int B, H, Sq, Sk, causal;
+  float scale;
+  // backward
+  const bf16* dO;
+  int64_t lddo;
+  float* D;  // [B, H, Sq]
+  bf16 *dq, *dk, *dv;
+  int64_t lddq, lddk, lddv;
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const bf16* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const bf16* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// 64 x 64 bf16 tile, rows [r0, r0+64) of a [nrows, ld] matrix, zero-filled past nrows
+__device__ __forceinline__ void load_tile(bf16* s, const bf16* g, int64_t ld, int r0, int nrows) {
+  for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r0 + r < nrows) v = *reinterpret_cast<const uint4*>(g + (int64_t)(r0 + r) * ld + c);
+    *reinterpret_cast<uint4*>(s + r * LDS + c) = v;
+  }
+}
+
+// A-operand fragments (16 rows x 64) for this warp's rows
+__device__ __forceinline__ void load_a_frags(uint32_t (&f)[4][4], const bf16* s, int warp, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+    ldsm_x4(f[ks], s + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8);
+}
+
+// acc[16 x 64 cols] = A(16 x 64) * Y^T where Y is a [64 cols][64 k] smem tile (k contiguous)
+__device__ __forceinline__ void mma_a_yt(float (&acc)[8][4], const uint32_t (&a)[4][4], const bf16* y, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      ldsm_x4(b, y + (np * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + ks * 16 + ((lane >> 3) & 1) * 8);
+      mma16816(acc[2 * np], a[ks], b[0], b[1]);
+      mma16816(acc[2 * np + 1], a[ks], b[2], b[3]);
+    }
+}
+
+// acc[16 x 64 dh] += P(16 x 64 k, C-fragment layout) * Y where Y is a [64 k][64 dh] smem tile
+__device__ __forceinline__ void mma_p_y(float (&acc)[8][4], const float (&pm)[8][4], const bf16* y, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4];
+    a[0] = pack2(pm[2 * ks][0], pm[2 * ks][1]);
+    a[1] = pack2(pm[2 * ks][2], pm[2 * ks][3]);
+    a[2] = pack2(pm[2 * ks + 1][0], pm[2 * ks + 1][1]);
+    a[3] = pack2(pm[2 * ks + 1][2], pm[2 * ks + 1][3]);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      ldsm_x4_t(b, y + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + np * 16 + (lane >> 4) * 8);
+      mma16816(acc[2 * np], a, b[0], b[1]);
+      mma16816(acc[2 * np + 1], a, b[2], b[3]);
+    }
+  }
+}
+
+__device__ __forceinline__ void store_rows(bf16* g, int64_t ld, int r_lo, int nrows, const float (&acc)[8][4], int lane,
+                                           float s_lo, float s_hi) {
+  const int t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int c = nt * 8 + 2 * t;
+    if (r_lo < nrows) *reinterpret_cast<uint32_t*>(g + (int64_t)r_lo * ld + c) = pack2(acc[nt][0] * s_lo, acc[nt][1] * s_lo);
+    if (r_lo + 8 < nrows) *reinterpret_cast<uint32_t*>(g + (int64_t)(r_lo + 8) * ld + c) = pack2(acc[nt][2] * s_hi, acc[nt][3] * s_hi);
+  }
+}
+
+// ------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
+  __shared__ __align__(16) bf16 sQ[TQ * LDS];
+  __shared__ __align__(16) bf16 sK[TK * LDS];
+  __shared__ __align__(16) bf16 sV[TK * LDS];
+  __shared__ uint8_t sPad[TK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
+  const bf16* qg = p.q + b * p.sbq + h * p.shq;
+  const bf16* kg = p.k + b * p.sbk + h * p.shk;
+  const bf16* vg = p.v + b * p.sbv + h * p.shv;
+  load_tile(sQ, qg, p.ldq, q0, p.Sq);
+  __syncthreads();
+  uint32_t qf[4][4];
+  load_a_frags(qf, sQ, warp, lane);
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+  const int r_lo = q0 + warp * 16 + g;
+  int kend = p.Sk;
+  if (p.causal && q0 + TQ < kend) kend = q0 + TQ;
+  for (int k0 = 0; k0 < kend; k0 += TK) {
+    __syncthreads();
+    load_tile(sK, kg, p.ldk, k0, p.Sk);
+    load_tile(sV, vg, p.ldv, k0, p.Sk);
+    if (threadIdx.x < TK) {
+      const int c = k0 + threadIdx.x;
+      sPad[threadIdx.x] = (c >= p.Sk) ? 1 : (p.key_pad ? p.key_pad[(int64_t)b * p.Sk + c] : 0);
+    }
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    mma_a_yt(s, qf, sK, lane);
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int cl = nt * 8 + 2 * t + (e & 1);
+        const int row = r_lo + (e >> 1) * 8;
+        const bool masked = sPad[cl] || (p.causal && (k0 + cl) > row);
+        const float v = masked ? -INFINITY : s[nt][e] * p.scale;
+        s[nt][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    float corr[2], mnew[2];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+      mnew[hh] = fmaxf(mrow[hh], mx[hh]);
+      corr[hh] = (mnew[hh] == -INFINITY) ? 1.f : __expf(mrow[hh] - mnew[hh]);
+      mrow[hh] = mnew[hh];
+      lrow[hh] *= corr[hh];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int hh = e >> 1;
+        const float pv = (mnew[hh] == -INFINITY) ? 0.f : __expf(s[nt][e] - mnew[hh]);
+        s[nt][e] = pv;
+        lrow[hh] += pv;
+        o[nt][e] *= corr[hh];
+      }
+    mma_p_y(o, s, sV, lane);
+  }
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    lrow[hh] += __shfl_xor_sync(0xffffffffu, lrow[hh], 1);
+    lrow[hh] += __shfl_xor_sync(0xffffffffu, lrow[hh], 2);
+  }
+  // a fully masked row yields NaN like the reference's softmax over all -inf
+  const float inv_lo = 1.f / lrow[0], inv_hi = 1.f / lrow[1];
+  bf16* og = p.o + b * p.sbo + h * p.sho;
+  store_rows(og, p.ldo, r_lo, p.Sq, o, lane, inv_lo, inv_hi);
+  if (p.lse && t == 0) {
+    float* l = p.lse + ((int64_t)b * p.H + h) * p.Sq;
+    if (r_lo < p.Sq) l[r_lo] = mrow[0] + __logf(lrow[0]);
+    if (r_lo + 8 < p.Sq) l[r_lo + 8] = mrow[1] + __logf(lrow[1]);
+  }
+}
+
+// ------------------------------------------------------------------ backward prep: D = rowsum(dO * O)
+__global__ void attn_bwd_prep_kernel(const AttnParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int total = p.B * p.H * p.Sq;
+  if (warp >= total) return;
+  const int i = warp % p.Sq, h = (warp / p.Sq) % p.H, b = warp / (p.Sq * p.H);
+  const bf16* o = p.o + ((int64_t)b * p.Sq + i) * p.ldo + h * DH;
+  const bf16* d = p.dO + ((int64_t)b * p.Sq + i) * p.lddo + h * DH;
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(o + 2 * lane);
+  const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(d + 2 * lane);
+  float v = __bfloat162float(a.x) * __bfloat162float(c.x) + __bfloat162float(a.y) * __bfloat162float(c.y);
+  v = warp_sum(v);
+  if (lane == 0) p.D[warp] = v;
+}
+
+// ------------------------------------------------------------------ backward, query-row owner: dQ
+__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
+  __shared__ __align__(16) bf16 sX[TQ * LDS];  // Q then dO (fragments are kept in registers)
+  __shared__ __align__(16) bf16 sK[TK * LDS];
+  __shared__ __align__(16) bf16 sV[TK * LDS];
+  __shared__ uint8_t sPad[TK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
+  const bf16* qg = p.q + b * p.sbq + h * p.shq;
+  const bf16* kg = p.k + b * p.sbk + h * p.shk;
+  const bf16* vg = p.v + b * p.sbv + h * p.shv;
+  const bf16* dog = p.dO + (int64_t)b * p.Sq * p.lddo + h * DH;
+  uint32_t qf[4][4], dof[4][4];
+  load_tile(sX, qg, p.ldq, q0, p.Sq);
+  __syncthreads();
+  load_a_frags(qf, sX, warp, lane);
+  __syncthreads();
+  load_tile(sX, dog, p.lddo, q0, p.Sq);
+  __syncthreads();
+  load_a_frags(dof, sX, warp, lane);
+  const int r_lo = q0 + warp * 16 + g;
+  const float* lse = p.lse + ((int64_t)b * p.H + h) * p.Sq;
+  const float* Dg = p.D + ((int64_t)b * p.H + h) * p.Sq;
+  float lrow[2], drow[2];
+  lrow[0] = r_lo < p.Sq ? lse[r_lo] : -INFINITY;
+  lrow[1] = r_lo + 8 < p.Sq ? lse[r_lo + 8] : -INFINITY;
+  drow[0] = r_lo < p.Sq ? Dg[r_lo] : 0.f;
+  drow[1] = r_lo + 8 < p.Sq ? Dg[r_lo + 8] : 0.f;
+  float dq[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+  int kend = p.Sk;
+  if (p.causal && q0 + TQ < kend) kend = q0 + TQ;
+  for (int k0 = 0; k0 < kend; k0 += TK) {
+    __syncthreads();
+    load_tile(sK, kg, p.ldk, k0, p.Sk);
+    load_tile(sV, vg, p.ldv, k0, p.Sk);
+    if (threadIdx.x < TK) {
+      const int c = k0 + threadIdx.x;
+      sPad[threadIdx.x] = (c >= p.Sk) ? 1 : (p.key_pad ? p.key_pad[(int64_t)b * p.Sk + c] : 0);
+    }
+    __syncthreads();
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+      dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+    }
+    mma_a_yt(s, qf, sK, lane);
+    mma_a_yt(dp, dof, sV, lane);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int cl = nt * 8 + 2 * t + (e & 1);
+        const int hh = e >> 1;
+        const int row = r_lo + hh * 8;
+        const bool masked = sPad[cl] || (p.causal && (k0 + cl) > row) || lrow[hh] == -INFINITY;
+        const float pv = masked ? 0.f : __expf(s[nt][e] * p.scale - lrow[hh]);
+        s[nt][e] = pv * (dp[nt][e] - drow[hh]) * p.scale;  // dS
+      }
+    mma_p_y(dq, s, sK, lane);
+  }
+  bf16* dqg = p.dq + (int64_t)b * p.Sq * p.lddq + h * DH;
+  store_rows(dqg, p.lddq, r_lo, p.Sq, dq, lane, 1.f, 1.f);
+}
+
+// ------------------------------------------------------------------ backward, key-row owner: dK, dV
+__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnParams p) {
+  __shared__ __align__(16) bf16 sX[TK * LDS];  // K then V of the owned rows
+  __shared__ __align__(16) bf16 sQ[TQ * LDS];
+  __shared__ __align__(16) bf16 sdO[TQ * LDS];
+  __shared__ float sL[TQ], sD[TQ];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int k0 = blockIdx.x * TK, h = blockIdx.y, b = blockIdx.z;
+  const bf16* qg = p.q + b * p.sbq + h * p.shq;
+  const bf16* kg = p.k + b * p.sbk + h * p.shk;
+  const bf16* vg = p.v + b * p.sbv + h * p.shv;
+  const bf16* dog = p.dO + (int64_t)b * p.Sq * p.lddo + h * DH;
+  const float* lse = p.lse + ((int64_t)b * p.H + h) * p.Sq;
+  const float* Dg = p.D + ((int64_t)b * p.H + h) * p.Sq;
+  uint32_t kf[4][4], vf[4][4];
+  load_tile(sX, kg, p.ldk, k0, p.Sk);
+  __syncthreads();
+  load_a_frags(kf, sX, warp, lane);
+  __syncthreads();
+  load_tile(sX, vg, p.ldv, k0, p.Sk);
+  __syncthreads();
+  load_a_frags(vf, sX, warp, lane);
+  const int r_lo = k0 + warp * 16 + g;  // key index of this thread's rows
+  bool rpad[2];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int r = r_lo + hh * 8;
+    rpad[hh] = (r >= p.Sk) || (p.key_pad && p.key_pad[(int64_t)b * p.Sk + r]);
+  }
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+    dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+  }
+  const int qstart = p.causal ? (k0 / TQ) * TQ : 0;  // queries before the key block see none of it
+  for (int q0 = qstart; q0 < p.Sq; q0 += TQ) {
+    __syncthreads();
+    load_tile(sQ, qg, p.ldq, q0, p.Sq);
+    load_tile(sdO, dog, p.lddo, q0, p.Sq);
+    if (threadIdx.x < TQ) {
+      const int r = q0 + threadIdx.x;
+      sL[threadIdx.x] = r < p.Sq ? lse[r] : -INFINITY;
+      sD[threadIdx.x] = r < p.Sq ? Dg[r] : 0.f;
+    }
+    __syncthreads();
+    float st[8][4], dpt[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+      dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
+    }
+    mma_a_yt(st, kf, sQ, lane);     // S^T = K Q^T
+    mma_a_yt(dpt, vf, sdO, lane);   // dP^T = V dO^T
+    float ds[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int cl = nt * 8 + 2 * t + (e & 1);  // query within block
+        const int hh = e >> 1;
+        const int key = r_lo + hh * 8;
+        const float l = sL[cl];
+        const bool masked = rpad[hh] || l == -INFINITY || (p.causal && key > (q0 + cl));
+        const float pv = masked ? 0.f : __expf(st[nt][e] * p.scale - l);
+        st[nt][e] = pv;                                        // P^T
+        ds[nt][e] = pv * (dpt[nt][e] - sD[cl]) * p.scale;      // dS^T
+      }
+    mma_p_y(dv, st, sdO, lane);
+    mma_p_y(dk, ds, sQ, lane);
+  }
+  bf16* dkg = p.dk + (int64_t)b * p.Sk * p.lddk + h * DH;
+  bf16* dvg = p.dv + (int64_t)b * p.Sk * p.lddv + h * DH;
+  store_rows(dkg, p.lddk, r_lo, p.Sk, dk, lane, 1.f, 1.f);
+  store_rows(dvg, p.lddv, r_lo, p.Sk, dv, lane, 1.f, 1.f);
+}
+
+static int check_attn_args(const AttnParams& p) {
+  if (!p.q || !p.k || !p.v || p.B <= 0 || p.H <= 0 || p.Sq <= 0 || p.Sk <= 0) return KMB_ERR_ARG;
+  if ((p.ldq % 8) || (p.ldk % 8) || (p.ldv % 8)) return KMB_ERR_ARG;
+  return KMB_OK;
+}
+
+}  // namespace kmb
+
+static void token_major_strides(kmb::AttnParams& p) {
+  p.sbq = (int64_t)p.Sq * p.ldq; p.shq = kmb::DH;
+  p.sbk = (int64_t)p.Sk * p.ldk; p.shk = kmb::DH;
+  p.sbv = (int64_t)p.Sk * p.ldv; p.shv = kmb::DH;
+  p.sbo = (int64_t)p.Sq * p.ldo; p.sho = kmb::DH;
+}
+
+extern "C" int kmb_attn_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                            void* o, int64_t ldo, float* lse, const uint8_t* key_pad, int B, int H, int Sq, int Sk,
+                            int head_dim, int causal, float scale, kmb_stream_t stream) {
+  using namespace kmb;
+  AttnParams p = {};
+  p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v;
+  p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.o = (bf16*)o; p.ldo = ldo; p.lse = lse; p.key_pad = key_pad;
+  p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal; p.scale = scale;
+  token_major_strides(p);
+  if (head_dim != DH || !o || (ldo % 8) || check_attn_args(p)) {
+    kmb_set_last_error("kmb_attn_fwd: bad argument (head_dim must be 64, strides multiples of 8)", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  dim3 grid((Sq + TQ - 1) / TQ, H, B);
+  attn_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+  KMB_CHECK_LAUNCH();
+  return KMB_OK;
+}
+
+// general-stride forward (no lse): q/o token-major or cache layout, see AttnParams
+extern "C" int kmb_attn_fwd_strided(const void* q, const void* k, const void* v, void* o, const int64_t* strides12,
+                                    const uint8_t* key_pad, int B, int H, int Sq, int Sk, int head_dim, int causal,
+                                    float scale, kmb_stream_t stream) {
+  using namespace kmb;
+  AttnParams p = {};
+  p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.o = (bf16*)o;
+  if (!strides12) { kmb_set_last_error("kmb_attn_fwd_strided: strides missing", __FILE__, __LINE__); return KMB_ERR_ARG; }
+  p.sbq = strides12[0]; p.shq = strides12[1]; p.ldq = strides12[2];
+  p.sbk = strides12[3]; p.shk = strides12[4]; p.ldk = strides12[5];
+  p.sbv = strides12[6]; p.shv = strides12[7]; p.ldv = strides12[8];
+  p.sbo = strides12[9]; p.sho = strides12[10]; p.ldo = strides12[11];
+  p.key_pad = key_pad; p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal; p.scale = scale;
+  bool bad = head_dim != DH || !o || check_attn_args(p);
+  for (int i = 0; i < 12; ++i) bad = bad || (strides12[i] % 8);
+  if (bad) { kmb_set_last_error("kmb_attn_fwd_strided: bad argument", __FILE__, __LINE__); return KMB_ERR_ARG; }
+  dim3 grid((Sq + TQ - 1) / TQ, H, B);
+  attn_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+  KMB_CHECK_LAUNCH();
+  return KMB_OK;
+}
+
+extern "C" int kmb_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                            const void* o, int64_t ldo, const void* d_o, int64_t lddo, const float* lse,
+                            float* d_scratch, const uint8_t* key_pad, void* dq, void* dk, void* dv, int64_t lddq,
+                            int64_t lddk, int64_t lddv, int B, int H, int Sq, int Sk, int head_dim, int causal,
+                            float scale, kmb_stream_t stream) {
+  using namespace kmb;
+  AttnParams p = {};
+  p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v;
+  p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.o = (bf16*)o; p.ldo = ldo; p.lse = (float*)lse; p.key_pad = key_pad;
+  p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal; p.scale = scale;
+  p.dO = (const bf16*)d_o; p.lddo = lddo; p.D = d_scratch;
+  p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
+  token_major_strides(p);
+  if (head_dim != DH || !o || !d_o || !lse || !d_scratch || !dq || !dk || !dv || (ldo % 8) || (lddo % 8) ||
+      (lddq % 2) || (lddk % 2) || (lddv % 2) || check_attn_args(p)) {
+    kmb_set_last_error("kmb_attn_bwd: bad argument", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = B * H * Sq;
+  attn_bwd_prep_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>(p);
+  KMB_CHECK_LAUNCH();
+  attn_bwd_dq_kernel<<<dim3((Sq + TQ - 1) / TQ, H, B), 128, 0, st>>>(p);
+  KMB_CHECK_LAUNCH();
+  attn_bwd_dkv_kernel<<<dim3((Sk + TK - 1) / TK, H, B), 128, 0, st>>>(p);
+  KMB_CHECK_LAUNCH();
+  return KMB_OK;
+}

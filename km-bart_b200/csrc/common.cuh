@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #define KMB_OK 0
 #define KMB_ERR_ARG (-1)

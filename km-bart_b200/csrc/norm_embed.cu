@@ -1,0 +1,616 @@
+// HBM-bound kernels around the GEMMs: RoI-feature packing, the multimodal embedding
+// (token gather | visual row + box projection) + position + LayerNorm (+dropout),
+// post-residual LayerNorm forward/backward with fused dropout re-masking and the
+// column reductions that produce LayerNorm / bias gradients, and the embedding backward.
+//
+// Reference call sites replaced:
+//   ImageEmbedding.forward cat + Linear ........ src/model/modules.py:24-41
+//   _embed_multi_modal gather / overwrite ...... src/model/modules.py:89-102
+//   + embed_positions + layernorm_embedding .... src/model/modules.py:133-137
+//   decoder embed + pos + LN ................... HF-3.0.2 BartDecoder.forward (src/model/model.py:87-97)
+//   residual + LayerNorm (post-LN) ............. HF-3.0.2 EncoderLayer / DecoderLayer
+// One warp owns one token row; a row (d <= 1024 fp32) stays in registers between the
+// statistics pass and the normalise pass, so each element is read once and written once.
+#include "common.cuh"
+#include "../../include/kmbart.h"
+
+namespace kmb {
+
+constexpr int FEAT = 2048;  // RoI feature width; the 4 box columns follow (src/data/dataset.py:44-47)
+constexpr int MAXV = 8;     // float4 per lane: d <= 1024
+
+struct DropCfg {
+  uint32_t thresh16;  // 0 = off
+  float scale;
+  uint32_t tag;
+  const uint64_t* seed;
+};
+
+__device__ __forceinline__ float4 drop4(float4 v, uint64_t seed, const DropCfg& dc, uint64_t q) {
+  const uint64_t bits = dropout_bits4(seed, dc.tag, q);
+  v.x = dropout_keep(bits, 0, dc.thresh16) ? v.x * dc.scale : 0.f;
+  v.y = dropout_keep(bits, 1, dc.thresh16) ? v.y * dc.scale : 0.f;
+  v.z = dropout_keep(bits, 2, dc.thresh16) ? v.z * dc.scale : 0.f;
+  v.w = dropout_keep(bits, 3, dc.thresh16) ? v.w * dc.scale : 0.f;
+  return v;
+}
+
+__device__ __forceinline__ uint2 pack4(float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  return make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+
+// ------------------------------------------------------------------ RoI feature packing
+// list-of-tensors [n_i, 2052] fp32 (pointer table) or one packed [R, 2052] fp32  ->
+// feats bf16 [R, 2048] (tensor-core operand) + boxes fp32 [R, 4] (kept exact: raw pixels)
+__global__ void __launch_bounds__(256) pack_features_kernel(const float* const* ptrs, const int* row_off, int B,
+                                                            const float* packed, bf16* feats, float* boxes, int R) {
+  const int r = blockIdx.x;
+  if (r >= R) return;
+  const float* src;
+  if (ptrs) {
+    int lo = 0, hi = B;  // largest b with row_off[b] <= r
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (row_off[mid] <= r) lo = mid; else hi = mid;
+    }
+    src = ptrs[lo] + (int64_t)(r - row_off[lo]) * (FEAT + 4);
+  } else {
+    src = packed + (int64_t)r * (FEAT + 4);
+  }
+  const int c = threadIdx.x * 8;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(src + c));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(src + c + 4));
+  const uint2 pa = pack4(a), pb = pack4(b);
+  *reinterpret_cast<uint4*>(feats + (int64_t)r * FEAT + c) = make_uint4(pa.x, pa.y, pb.x, pb.y);
+  if (threadIdx.x == 0)
+    *reinterpret_cast<float4*>(boxes + (int64_t)r * 4) = __ldg(reinterpret_cast<const float4*>(src + FEAT));
+}
+
+// slot_idx[b, s] = packed RoI row that overwrites token (b, s), or -1 (src/model/modules.py:91,98-100)
+__global__ void slot_index_kernel(const int64_t* ids, const int* row_off, int S, int img_feat_id, int cls_id,
+                                  int* slot_idx) {
+  const int b = blockIdx.x;
+  __shared__ int warp_cnt[32];
+  __shared__ int running;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  for (int s0 = 0; s0 < S; s0 += blockDim.x) {
+    const int s = s0 + threadIdx.x;
+    int flag = 0;
+    if (s < S) {
+      const int64_t t = ids[(int64_t)b * S + s];
+      flag = (t == img_feat_id || t == cls_id);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) warp_cnt[w] = __popc(bal);
+    __syncthreads();
+    int before = running;
+    for (int i = 0; i < w; ++i) before += warp_cnt[i];
+    const int rank = before + __popc(bal & ((1u << lane) - 1));
+    if (s < S) {
+      const int n_b = row_off[b + 1] - row_off[b];
+      slot_idx[(int64_t)b * S + s] = (flag && rank < n_b) ? row_off[b] + rank : -1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += warp_cnt[i];
+      running += tot;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ embedding + LN forward
+struct EmbedParams {
+  const int64_t* ids;     // [M]
+  const int* slot_idx;    // [M] or null (decoder)
+  const float* tok_emb;   // [V, d] fp32 master
+  const float* pos_emb;   // [npos, d]
+  const float* vis_acc;   // [R, d] fp32: feats . Wfeat^T (no bias)
+  const float* boxes;     // [R, 4]
+  const float* w_box;     // [d, 4]
+  const float* b_img;     // [d]
+  const float* gamma;
+  const float* beta;
+  float* pre;             // [M, d] LN input (kept for backward) or null
+  float* out_f32;         // [M, d]
+  bf16* out_bf16;         // [M, d]
+  float* mean;            // [M]
+  float* rstd;            // [M]
+  int M, S, d, pos_offset;
+  const int* pos_index;   // device scalar: explicit position for every row (cached decode) or null
+  float embed_scale;
+  DropCfg drop;
+};
+
+template <int NV>
+__global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const EmbedParams p) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= p.M) return;
+  const int d = p.d;
+  const int s = p.pos_index ? *p.pos_index : row % p.S;
+  const int slot = p.slot_idx ? p.slot_idx[row] : -1;
+  const float* pos = p.pos_emb + (int64_t)(s + p.pos_offset) * d;
+  float4 x[NV];
+  if (slot >= 0) {
+    const float* va = p.vis_acc + (int64_t)slot * d;
+    const float4 bx = __ldg(reinterpret_cast<const float4*>(p.boxes + (int64_t)slot * 4));
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(va + c));
+        const float4 bi = __ldg(reinterpret_cast<const float4*>(p.b_img + c));
+        float o[4] = {v.x + bi.x, v.y + bi.y, v.z + bi.z, v.w + bi.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(p.w_box + (int64_t)(c + j) * 4));
+          o[j] += bx.x * w.x + bx.y * w.y + bx.z * w.z + bx.w * w.w;
+        }
+        x[i] = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  } else {
+    const float* te = p.tok_emb + (int64_t)p.ids[row] * d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) x[i] = __ldg(reinterpret_cast<const float4*>(te + c));
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) {
+      const float4 pe = __ldg(reinterpret_cast<const float4*>(pos + c));
+      x[i].x = x[i].x * p.embed_scale + pe.x;
+      x[i].y = x[i].y * p.embed_scale + pe.y;
+      x[i].z = x[i].z * p.embed_scale + pe.z;
+      x[i].w = x[i].w * p.embed_scale + pe.w;
+      sum += x[i].x + x[i].y + x[i].z + x[i].w;
+      if (p.pre) *reinterpret_cast<float4*>(p.pre + (int64_t)row * d + c) = x[i];
+    }
+  }
+  const float mean = warp_sum(sum) / d;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) {
+      const float a = x[i].x - mean, b = x[i].y - mean, cc = x[i].z - mean, e = x[i].w - mean;
+      var += a * a + b * b + cc * cc + e * e;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(var) / d + 1e-5f);
+  if (lane == 0) {
+    if (p.mean) p.mean[row] = mean;
+    if (p.rstd) p.rstd[row] = rstd;
+  }
+  const uint64_t seed = p.drop.thresh16 ? *p.drop.seed : 0ull;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta + c));
+      float4 y;
+      y.x = (x[i].x - mean) * rstd * g.x + b.x;
+      y.y = (x[i].y - mean) * rstd * g.y + b.y;
+      y.z = (x[i].z - mean) * rstd * g.z + b.z;
+      y.w = (x[i].w - mean) * rstd * g.w + b.w;
+      if (p.drop.thresh16) y = drop4(y, seed, p.drop, ((uint64_t)row * d + c) >> 2);
+      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (int64_t)row * d + c) = y;
+      if (p.out_bf16) *reinterpret_cast<uint2*>(p.out_bf16 + (int64_t)row * d + c) = pack4(y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm forward
+template <int NV>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float* out_f32, bf16* out_bf16,
+                                                     float* mean_o, float* rstd_o, int M, int d) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float4 x[NV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) {
+      x[i] = *reinterpret_cast<const float4*>(pre + (int64_t)row * d + c);
+      sum += x[i].x + x[i].y + x[i].z + x[i].w;
+    }
+  }
+  const float mean = warp_sum(sum) / d;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) {
+      const float a = x[i].x - mean, b = x[i].y - mean, cc = x[i].z - mean, e = x[i].w - mean;
+      var += a * a + b * b + cc * cc + e * e;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(var) / d + 1e-5f);
+  if (lane == 0) {
+    if (mean_o) mean_o[row] = mean;
+    if (rstd_o) rstd_o[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float4 y;
+      y.x = (x[i].x - mean) * rstd * g.x + b.x;
+      y.y = (x[i].y - mean) * rstd * g.y + b.y;
+      y.z = (x[i].z - mean) * rstd * g.z + b.z;
+      y.w = (x[i].w - mean) * rstd * g.w + b.w;
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + (int64_t)row * d + c) = y;
+      if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + (int64_t)row * d + c) = pack4(y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm backward
+// dy  : grad w.r.t. the LN output (fp32).  If drop_in is on, the forward applied dropout to
+//       the LN output (embedding LN), so dy is re-masked on read.
+// dpre: grad w.r.t. the LN input (fp32) — the residual-stream gradient.
+// dz  : bf16 copy of dpre, re-masked with drop_out (the dropout that sat between the preceding
+//       Linear and the residual add) — the dY operand of that Linear's dgrad / wgrad GEMMs.
+// dgamma/dbeta/dbias (+=): column sums of dy*xhat, dy, dz.  Zero them before the first call.
+struct LnBwdParams {
+  const float* dy;
+  const float* pre;
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  float* dpre;
+  bf16* dz;
+  float* dgamma;
+  float* dbeta;
+  float* dbias;
+  int M, d;
+  DropCfg drop_in, drop_out;
+};
+
+template <int NV>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int d = p.d;
+  float4 ag[NV], ab[NV], az[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = az[i] = make_float4(0, 0, 0, 0);
+  const uint64_t seed_in = p.drop_in.thresh16 ? *p.drop_in.seed : 0ull;
+  const uint64_t seed_out = p.drop_out.thresh16 ? *p.drop_out.seed : 0ull;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < p.M; row += nwarps) {
+    const float mean = p.mean[row], rstd = p.rstd[row];
+    float4 g[NV], xh[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        float4 dy = *reinterpret_cast<const float4*>(p.dy + (int64_t)row * d + c);
+        if (p.drop_in.thresh16) dy = drop4(dy, seed_in, p.drop_in, ((uint64_t)row * d + c) >> 2);
+        const float4 x = *reinterpret_cast<const float4*>(p.pre + (int64_t)row * d + c);
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
+        xh[i] = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
+        g[i] = make_float4(dy.x * gm.x, dy.y * gm.y, dy.z * gm.z, dy.w * gm.w);
+        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+        s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+        ag[i].x += dy.x * xh[i].x; ag[i].y += dy.y * xh[i].y; ag[i].z += dy.z * xh[i].z; ag[i].w += dy.w * xh[i].w;
+        ab[i].x += dy.x; ab[i].y += dy.y; ab[i].z += dy.z; ab[i].w += dy.w;
+      }
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        float4 dx;
+        dx.x = rstd * (g[i].x - s1 - xh[i].x * s2);
+        dx.y = rstd * (g[i].y - s1 - xh[i].y * s2);
+        dx.z = rstd * (g[i].z - s1 - xh[i].z * s2);
+        dx.w = rstd * (g[i].w - s1 - xh[i].w * s2);
+        if (p.dpre) *reinterpret_cast<float4*>(p.dpre + (int64_t)row * d + c) = dx;
+        if (p.dz || p.dbias) {
+          float4 z = dx;
+          if (p.drop_out.thresh16) z = drop4(z, seed_out, p.drop_out, ((uint64_t)row * d + c) >> 2);
+          if (p.dz) *reinterpret_cast<uint2*>(p.dz + (int64_t)row * d + c) = pack4(z);
+          az[i].x += z.x; az[i].y += z.y; az[i].z += z.z; az[i].w += z.w;
+        }
+      }
+    }
+  }
+  // block-level column reduction through shared memory, then one atomic per column per block
+  __shared__ float4 red[8][32];
+  for (int which = 0; which < 3; ++which) {
+    float* dst = which == 0 ? p.dgamma : (which == 1 ? p.dbeta : p.dbias);
+    if (!dst) continue;  // uniform across the block
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 v = which == 0 ? ag[i] : (which == 1 ? ab[i] : az[i]);
+      red[wib][lane] = v;
+      __syncthreads();
+      if (wib == 0) {
+        float4 t = red[0][lane];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+          const float4 u = red[w][lane];
+          t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        const int c = (i * 32 + lane) * 4;
+        if (c < d) {
+          atomicAdd(dst + c, t.x); atomicAdd(dst + c + 1, t.y); atomicAdd(dst + c + 2, t.z); atomicAdd(dst + c + 3, t.w);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ embedding backward
+// demb fp32 [M, d] = grad w.r.t. (tok|vis)*scale + pos.  Token rows scatter-add into the shared
+// embedding gradient (skipping padding_idx like nn.Embedding), visual rows are written to
+// dvis (bf16 for the wgrad GEMM); positions are reduced over the batch without atomics.
+__global__ void __launch_bounds__(256) embed_bwd_scatter_kernel(const float* demb, const int64_t* ids, const int* slot_idx,
+                                                                float* d_tok, bf16* dvis, int M, int d, int pad_id,
+                                                                float embed_scale) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int slot = slot_idx ? slot_idx[row] : -1;
+  const int64_t tok = ids[row];
+  for (int c = lane * 4; c < d; c += 128) {
+    float4 v = *reinterpret_cast<const float4*>(demb + (int64_t)row * d + c);
+    v.x *= embed_scale; v.y *= embed_scale; v.z *= embed_scale; v.w *= embed_scale;
+    if (slot >= 0) {
+      *reinterpret_cast<uint2*>(dvis + (int64_t)slot * d + c) = pack4(v);
+    } else if (tok != pad_id) {
+      float* dst = d_tok + tok * d + c;
+      atomicAdd(dst, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+    }
+  }
+}
+
+// dpos[s + off, :] (+)= sum_b demb[b, s, :]
+__global__ void pos_grad_kernel(const float* demb, float* dpos, int B, int S, int d, int pos_offset, int accumulate) {
+  const int s = blockIdx.x;
+  for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
+    float4 acc = make_float4(0, 0, 0, 0);
+    for (int b = 0; b < B; ++b) {
+      const float4 v = *reinterpret_cast<const float4*>(demb + ((int64_t)b * S + s) * d + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float4* dst = reinterpret_cast<float4*>(dpos + (int64_t)(s + pos_offset) * d + c);
+    if (accumulate) {
+      const float4 o = *dst;
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    *dst = acc;
+  }
+}
+
+// dW_img[:, 2048:2052] and the fp32 column sums for the box path:
+// dWbox[c, j] += sum_r dvis[r, c] * box[r, j]
+__global__ void box_wgrad_kernel(const bf16* dvis, const float* boxes, float* dw_img, int R, int d, int ld_w,
+                                 int rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(R, r0 + rows_per_block);
+  float a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  for (int r = r0; r < r1; ++r) {
+    const float g = __bfloat162float(dvis[(int64_t)r * d + c]);
+    const float4 bx = __ldg(reinterpret_cast<const float4*>(boxes + (int64_t)r * 4));
+    a0 += g * bx.x; a1 += g * bx.y; a2 += g * bx.z; a3 += g * bx.w;
+  }
+  float* dst = dw_img + (int64_t)c * ld_w + FEAT;
+  atomicAdd(dst, a0); atomicAdd(dst + 1, a1); atomicAdd(dst + 2, a2); atomicAdd(dst + 3, a3);
+}
+
+// out[n] += sum_m x[m, n]   (bf16 in, fp32 out) — bias gradients of qkv / fc1 / heads
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* x, int64_t ld, float* out, int M, int N,
+                                                          int rows_per_block) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (c >= N) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float a = 0.f, b = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + (int64_t)r * ld + c);
+    a += __bfloat162float(v.x);
+    b += __bfloat162float(v.y);
+  }
+  atomicAdd(out + c, a);
+  if (c + 1 < N) atomicAdd(out + c + 1, b);
+}
+
+// gather rows: out[i, :] = src[idx[i], :] (bf16), used by the pretraining heads
+__global__ void gather_rows_bf16_kernel(const bf16* src, int64_t ld_src, const int* idx, bf16* out, int64_t ld_out,
+                                        int n, int d) {
+  const int row = blockIdx.x;
+  if (row >= n) return;
+  const int s = idx[row];
+  for (int c = threadIdx.x * 8; c < d; c += blockDim.x * 8)
+    *reinterpret_cast<uint4*>(out + (int64_t)row * ld_out + c) =
+        *reinterpret_cast<const uint4*>(src + (int64_t)s * ld_src + c);
+}
+
+// scatter-add rows: dst[idx[i], :] += src[i, :] (bf16 src, fp32 dst) — head gradients back into dH
+__global__ void scatter_add_rows_kernel(const bf16* src, int64_t ld_src, const int* idx, float* dst, int64_t ld_dst,
+                                        int n, int d) {
+  const int row = blockIdx.x;
+  if (row >= n) return;
+  const int t = idx[row];
+  for (int c = threadIdx.x; c < d; c += blockDim.x)
+    atomicAdd(dst + (int64_t)t * ld_dst + c, __bfloat162float(src[(int64_t)row * ld_src + c]));
+}
+
+static DropCfg make_drop(float p, uint32_t tag, const uint64_t* seed) {
+  DropCfg dc;
+  dc.thresh16 = (p > 0.f && seed) ? (uint32_t)(p * 65536.0f + 0.5f) : 0;
+  dc.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  dc.tag = tag;
+  dc.seed = seed;
+  return dc;
+}
+
+}  // namespace kmb
+
+using namespace kmb;
+
+extern "C" int kmb_pack_features(const float* const* feat_ptrs, const int* row_offsets, int B, const float* packed,
+                                 void* feats_bf16, float* boxes, int R, kmb_stream_t stream) {
+  if ((!feat_ptrs && !packed) || (feat_ptrs && !row_offsets) || !feats_bf16 || !boxes || R < 0) {
+    kmb_set_last_error("kmb_pack_features: bad argument", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  if (R == 0) return KMB_OK;
+  pack_features_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(feat_ptrs, row_offsets, B, packed, (bf16*)feats_bf16, boxes, R);
+  KMB_CHECK_LAUNCH();
+  return KMB_OK;
+}
+
+extern "C" int kmb_slot_index(const int64_t* input_ids, const int* row_offsets, int B, int S, int img_feat_id,
+                              int cls_token_id, int* slot_idx, kmb_stream_t stream) {
+  if (!input_ids || !row_offsets || !slot_idx || B <= 0 || S <= 0) {
+    kmb_set_last_error("kmb_slot_index: bad argument", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  slot_index_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(input_ids, row_offsets, S, img_feat_id, cls_token_id, slot_idx);
+  KMB_CHECK_LAUNCH();
+  return KMB_OK;
+}
+
+#define KMB_DISPATCH_NV(d, CALL6, CALL8)                                              \
+  if ((d) % 128 == 0 && (d) <= 768) { CALL6; }                                        \
+  else if ((d) % 4 == 0 && (d) <= 1024) { CALL8; }                                    \
+  else { kmb_set_last_error("d_model must be a multiple of 4 and <= 1024", __FILE__, __LINE__); return KMB_ERR_ARG; }
+
+extern "C" int kmb_embed_ln_fwd(const int64_t* ids, const int* slot_idx, const float* tok_emb, const float* pos_emb,
+                                const float* vis_acc, const float* boxes, const float* w_box, const float* b_img,
+                                const float* gamma, const float* beta, float* pre, float* out_f32, void* out_bf16,
+                                float* mean, float* rstd, int M, int S, int d, int pos_offset, const int* pos_index,
+                                float embed_scale, float dropout_p, uint32_t dropout_tag, const uint64_t* dropout_seed,
+                                kmb_stream_t stream) {
+  if (!ids || !tok_emb || !pos_emb || !gamma || !beta || M <= 0 || S <= 0) {
+    kmb_set_last_error("kmb_embed_ln_fwd: bad argument", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  EmbedParams p;
+  p.ids = ids; p.slot_idx = slot_idx; p.tok_emb = tok_emb; p.pos_emb = pos_emb; p.vis_acc = vis_acc; p.boxes = boxes;
+  p.w_box = w_box; p.b_img = b_img; p.gamma = gamma; p.beta = beta; p.pre = pre; p.out_f32 = out_f32;
+  p.out_bf16 = (bf16*)out_bf16; p.mean = mean; p.rstd = rstd; p.M = M; p.S = S; p.d = d; p.pos_offset = pos_offset;
+  p.pos_index = pos_index; p.embed_scale = embed_scale; p.drop = make_drop(dropout_p, dropout_tag, dropout_seed);
+  const int blocks = (M * 32 + 255) / 256;
+  cudaStream_t st = (cudaStream_t)stream;
+  KMB_DISPATCH_NV(d, (embed_ln_fwd_kernel<6><<<blocks, 256, 0, st>>>(p)), (embed_ln_fwd_kernel<8><<<blocks, 256, 0, st>>>(p)));
+  KMB_CHECK_LAUNCH();
+  return KMB_OK;
+}
+
+extern "C" int kmb_layernorm_fwd(const float* pre, const float* gamma, const float* beta, float* out_f32,
+                                 void* out_bf16, float* mean, float* rstd, int M, int d, kmb_stream_t stream) {
+  if (!pre || !gamma || !beta || M <= 0) {
+    kmb_set_last_error("kmb_layernorm_fwd: bad argument", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  const int blocks = (M * 32 + 255) / 256;
+  cudaStream_t st = (cudaStream_t)stream;
+  KMB_DISPATCH_NV(d, (ln_fwd_kernel<6><<<blocks, 256, 0, st>>>(pre, gamma, beta, out_f32, (bf16*)out_bf16, mean, rstd, M, d)),
+                  (ln_fwd_kernel<8><<<blocks, 256, 0, st>>>(pre, gamma, beta, out_f32, (bf16*)out_bf16, mean, rstd, M, d)));
+  KMB_CHECK_LAUNCH();
+  return KMB_OK;
+}
+
+extern "C" int kmb_layernorm_bwd(const float* dy, const float* pre, const float* mean, const float* rstd,
+                                 const float* gamma, float* dpre, void* dz_bf16, float* dgamma, float* dbeta,
+                                 float* dbias, int M, int d, float drop_in_p, uint32_t drop_in_tag, float drop_out_p,
+                                 uint32_t drop_out_tag, const uint64_t* dropout_seed, kmb_stream_t stream) {
+  if (!dy || !pre || !mean || !rstd || !gamma || M <= 0) {
+    kmb_set_last_error("kmb_layernorm_bwd: bad argument", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  LnBwdParams p;
+  p.dy = dy; p.pre = pre; p.mean = mean; p.rstd = rstd; p.gamma = gamma; p.dpre = dpre; p.dz = (bf16*)dz_bf16;
+  p.dgamma = dgamma; p.dbeta = dbeta; p.dbias = dbias; p.M = M; p.d = d;
+  p.drop_in = make_drop(drop_in_p, drop_in_tag, dropout_seed);
+  p.drop_out = make_drop(drop_out_p, drop_out_tag, dropout_seed);
+  int blocks = (M + 7) / 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  KMB_DISPATCH_NV(d, (ln_bwd_kernel<6><<<blocks, 256, 0, st>>>(p)), (ln_bwd_kernel<8><<<blocks, 256, 0, st>>>(p)));
+  KMB_CHECK_LAUNCH();
+  return KMB_OK;
+}
+
+extern "C" int kmb_embed_bwd(const float* demb, const int64_t* ids, const int* slot_idx, float* d_tok, void* dvis_bf16,
+                             float* dpos, int B, int S, int d, int pos_offset, int pad_id, float embed_scale,
+                             int accumulate_pos, kmb_stream_t stream) {
+  if (!demb || !ids || !d_tok || !dpos || B <= 0 || S <= 0 || (d % 4)) {
+    kmb_set_last_error("kmb_embed_bwd: bad argument", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = B * S;
+  embed_bwd_scatter_kernel<<<(M * 32 + 255) / 256, 256, 0, st>>>(demb, ids, slot_idx, d_tok, (bf16*)dvis_bf16, M, d, pad_id, embed_scale);
+  KMB_CHECK_LAUNCH();
+  pos_grad_kernel<<<S, 192, 0, st>>>(demb, dpos, B, S, d, pos_offset, accumulate_pos);
+  KMB_CHECK_LAUNCH();
+  return KMB_OK;
+}
+
+extern "C" int kmb_box_wgrad(const void* dvis_bf16, const float* boxes, float* dw_img, int R, int d, int ld_w,
+                             kmb_stream_t stream) {
+  if (!dvis_bf16 || !boxes || !dw_img || R <= 0) {
+    kmb_set_last_error("kmb_box_wgrad: bad argument", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  const int rpb = 128;
+  box_wgrad_kernel<<<dim3((d + 127) / 128, (R + rpb - 1) / rpb), 128, 0, (cudaStream_t)stream>>>((const bf16*)dvis_bf16, boxes, dw_img, R, d, ld_w, rpb);
+  KMB_CHECK_LAUNCH();
+  return KMB_OK;
+}
+
+extern "C" int kmb_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, kmb_stream_t stream) {
+  if (!x || !out || M <= 0 || N <= 0 || (ld % 2) || (N % 2)) {
+    kmb_set_last_error("kmb_colsum_bf16: bad argument", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  const int rpb = 64;
+  colsum_bf16_kernel<<<dim3((N / 2 + 255) / 256, (M + rpb - 1) / rpb), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld, out, M, N, rpb);
+  KMB_CHECK_LAUNCH();
+  return KMB_OK;
+}
+
+extern "C" int kmb_gather_rows_bf16(const void* src, int64_t ld_src, const int* idx, void* out, int64_t ld_out, int n,
+                                    int d, kmb_stream_t stream) {
+  if (!src || !idx || !out || n < 0 || (d % 8) || (ld_src % 8) || (ld_out % 8)) {
+    kmb_set_last_error("kmb_gather_rows_bf16: bad argument", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  if (n == 0) return KMB_OK;
+  gather_rows_bf16_kernel<<<n, 128, 0, (cudaStream_t)stream>>>((const bf16*)src, ld_src, idx, (bf16*)out, ld_out, n, d);
+  KMB_CHECK_LAUNCH();
+  return KMB_OK;
+}
+
+extern "C" int kmb_scatter_add_rows(const void* src_bf16, int64_t ld_src, const int* idx, float* dst, int64_t ld_dst,
+                                    int n, int d, kmb_stream_t stream) {
+  if (!src_bf16 || !idx || !dst || n < 0) {
+    kmb_set_last_error("kmb_scatter_add_rows: bad argument", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  if (n == 0) return KMB_OK;
+  scatter_add_rows_kernel<<<n, 256, 0, (cudaStream_t)stream>>>((const bf16*)src_bf16, ld_src, idx, dst, ld_dst, n, d);
+  KMB_CHECK_LAUNCH();
+  return KMB_OK;
+}

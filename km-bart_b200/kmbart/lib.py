@@ -1,0 +1,118 @@
+"""ctypes binding of libkmbart_sm100.so (C-ABI declared in include/kmbart.h).
+
+The product path has NO fallback: if the shared library is missing or the device is not
+sm_100, importing the kernels raises.  Build with `python __graft_entry__.py` / `make`.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libkmbart_sm100.so")
+
+c_void_p, c_int, c_int64, c_float, c_uint32 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32
+
+EPI_LINEAR, EPI_CE_STATS, EPI_CE_GRAD = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_GELU_GRAD, ACT_TANH, ACT_TANH_GRAD = 0, 1, 2, 3, 4
+
+
+class GemmEpilogue(C.Structure):
+    """Mirror of struct KmbGemmEpilogue."""
+    _fields_ = [
+        ("mode", C.c_int32), ("act", C.c_int32), ("alpha", c_float), ("accumulate", C.c_int32),
+        ("bias", c_void_p), ("residual", c_void_p), ("ld_res", c_int64),
+        ("aux", c_void_p), ("ld_aux", c_int64),
+        ("out_f32", c_void_p), ("ld_f32", c_int64),
+        ("out_bf16", c_void_p), ("ld_bf16", c_int64), ("out_preact", c_void_p),
+        ("dropout_p", c_float), ("dropout_tag", c_uint32), ("dropout_seed", c_void_p),
+        ("labels", c_void_p), ("ce_max", c_void_p), ("ce_sum", c_void_p), ("ce_label_logit", c_void_p),
+        ("ce_lse", c_void_p), ("ce_gscale", c_void_p),
+    ]
+
+
+# name -> argtypes; every function returns int except those listed in _RESTYPES
+_PROTOS = {
+    "kmb_version": [],
+    "kmb_arch_check": [],
+    "kmb_gemm": [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int, c_int, c_int,
+                 C.POINTER(GemmEpilogue), c_int, c_void_p],
+    "kmb_gemm_n_tiles": [c_int, c_int],
+    "kmb_gemm_pick_tile_n": [c_int, c_int],
+    "kmb_attn_fwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+                     c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "kmb_attn_fwd_strided": [c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_int64), c_void_p,
+                             c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "kmb_attn_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                     c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "kmb_pack_features": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "kmb_slot_index": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "kmb_embed_ln_fwd": [c_void_p] * 15 + [c_int, c_int, c_int, c_int, c_void_p, c_float, c_float, c_uint32,
+                                           c_void_p, c_void_p],
+    "kmb_embed_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                      c_float, c_int, c_void_p],
+    "kmb_box_wgrad": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "kmb_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "kmb_layernorm_bwd": [c_void_p] * 10 + [c_int, c_int, c_float, c_uint32, c_float, c_uint32, c_void_p, c_void_p],
+    "kmb_colsum_bf16": [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p],
+    "kmb_gather_rows_bf16": [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p],
+    "kmb_scatter_add_rows": [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p],
+    "kmb_ce_combine": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float,
+                       c_void_p, c_void_p, c_int, c_void_p],
+    "kmb_ce_gscale": [c_void_p, c_void_p, c_float, c_void_p, c_void_p],
+    "kmb_small_xent": [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_float, c_void_p,
+                       c_void_p, c_int64, c_void_p, c_void_p],
+    "kmb_adamw_chunk_elems": [],
+    "kmb_adamw_multi": [c_void_p, c_void_p, c_int, c_void_p, c_float, c_float, c_float, c_float, c_float, c_int,
+                        c_void_p, c_void_p],
+    "kmb_cast_bf16": [c_void_p, c_void_p, c_int64, c_void_p],
+    "kmb_repack_img_weight": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "kmb_invert_mask": [c_void_p, c_void_p, c_int64, c_void_p],
+    "kmb_next_seed": [c_void_p, c_void_p, c_void_p],
+    "kmb_split_tf32": [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p],
+}
+_RESTYPES = {"kmb_last_error": C.c_char_p}
+
+EXPORTED_SYMBOLS = sorted(list(_PROTOS) + ["kmb_last_error"])
+
+_lib = None
+
+
+class KmbartError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the library once; raise (never fall back) if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KmbartError(
+            f"{LIB_PATH} not found: the sm_100a CUDA library is required (no CPU fallback). "
+            "Build it with `python __graft_entry__.py` or `make` at the repo root.")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = c_int
+    lib.kmb_last_error.argtypes = []
+    lib.kmb_last_error.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().kmb_last_error().decode(errors="replace")
+        raise KmbartError(f"{what} failed with code {rc}: {msg}")
+
+
+_arch_ok = False
+
+
+def require_b200():
+    """Hard gate used by every GPU entry point."""
+    global _arch_ok
+    if not _arch_ok:
+        check(load().kmb_arch_check(), "kmb_arch_check")
+        _arch_ok = True
