@@ -2,9 +2,10 @@
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "km-bart_b200"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 from oracle import kmbart_oracle as O
-from tests.helpers import small_config, product_config, load_oracle_weights, to_cuda_batch, rel_err
+from helpers import small_config, product_config, load_oracle_weights, to_cuda_batch, rel_err
 from src.model.model import MultiModalBartForConditionalGeneration
 
 torch.manual_seed(0)
