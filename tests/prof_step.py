@@ -1,0 +1,33 @@
+"""Profiling driver: config-2 train step; warm-up outside, N profiled steps inside cudaProfilerStart/Stop.
+   ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file X python tests/prof_step.py"""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "km-bart_b200"))
+import torch
+import bench
+from src.model.config import MultiModalBartConfig
+from src.model.model import MultiModalBartForConditionalGeneration
+from kmbart.optim import AdamW
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+cfg = MultiModalBartConfig.from_dict(json.load(open(os.path.join(ROOT, "configs", "vcg_base.json"))))
+torch.manual_seed(0)
+model = MultiModalBartForConditionalGeneration(cfg).cuda().train()
+opt = AdamW(model.parameters(), lr=1e-5)
+batch = bench.make_batch(cfg, 1234, device="cuda")
+
+def step():
+    loss = model(**batch)[0]
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+for _ in range(steps):
+    step()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
+print("done")
