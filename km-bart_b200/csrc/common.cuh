@@ -189,10 +189,30 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 31;
   return x;
 }
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352dU;
+  x ^= x >> 15;
+  x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
+}
+// per-kernel key folded from (seed, tag); computed once per thread
+__host__ __device__ __forceinline__ uint32_t dropout_key(uint64_t seed, uint32_t tag) {
+  return hash32((uint32_t)seed ^ hash32((uint32_t)(seed >> 32) + tag * 0x9E3779B1U));
+}
 // returns 4 x 16 random bits for elements [4*q, 4*q+3]
 __host__ __device__ __forceinline__ uint64_t dropout_bits4(uint64_t seed, uint32_t tag,
                                                            uint64_t q) {
-  return mix64(seed ^ mix64(((uint64_t)tag << 40) ^ q ^ 0x9E3779B97F4A7C15ULL));
+  const uint32_t k = dropout_key(seed, tag);
+  const uint32_t lo = hash32(((uint32_t)q * 2u) ^ k);
+  const uint32_t hi = hash32(((uint32_t)q * 2u + 1u) ^ k);
+  return ((uint64_t)hi << 32) | lo;
+}
+__host__ __device__ __forceinline__ uint64_t dropout_bits4_k(uint32_t key, uint64_t q) {
+  const uint32_t lo = hash32(((uint32_t)q * 2u) ^ key);
+  const uint32_t hi = hash32(((uint32_t)q * 2u + 1u) ^ key);
+  return ((uint64_t)hi << 32) | lo;
 }
 // keep iff 16-bit lane >= thresh16 (thresh16 = round(p * 65536))
 __host__ __device__ __forceinline__ bool dropout_keep(uint64_t bits4, int lane, uint32_t thresh16) {

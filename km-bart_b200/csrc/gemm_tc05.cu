@@ -1,10 +1,11 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a:  D[M,N] = epilogue(sum_k A(m,k) * B(n,k)).
 //
-// One persistent CTA per SM, 256 threads, warp-specialised:
+// One persistent CTA per SM, 384 threads, warp-specialised:
 //   warp 0      TMA producer   (one elected lane; cp.async.bulk.tensor 2D, SWIZZLE_128B)
 //   warp 1      MMA issuer     (one elected lane; tcgen05.mma cta_group::1, M=128, N=BN, K=16|8)
 //   warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns)
-//   warps 4..7  epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//   warps 4..11 epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> swizzled smem
+//                               transpose -> coalesced global I/O)
 // Three mbarrier pipelines: smem full/empty (TMA<->MMA), tmem full/empty (MMA<->epilogue),
 // and a static round-robin tile schedule.  Operands may be K-major or MN-major (the
 // backward GEMMs contract over the token dimension, which is the slow dimension of
@@ -37,10 +38,11 @@ template <int BN>
 struct Cfg {
   static constexpr int B_TILE_BYTES = BN * TILE_BYTES_ROW;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES_RAW = (227 * 1024 - 2048) / STAGE_BYTES;
+  static constexpr int EPI_STAGING = 8 * 4096;  // one 32x32 fp32 transpose tile per epilogue warp
+  static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 256 - EPI_STAGING) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_STAGING;
 };
 
 // Instruction descriptor, field layout per cute/arch/mma_sm100_desc.hpp InstrDescriptor.
@@ -64,13 +66,86 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// ------------------------------------------------------------------ epilogue: 32 columns of one row
-template <int BN>
-__device__ __forceinline__ void epilogue_linear(const GemmParams& p, float (&v)[32], int row,
-                                                int col0, int ncols /*valid cols in chunk*/,
-                                                uint64_t seed) {
+// ------------------------------------------------------------------ epilogue staging
+// Each epilogue warp owns a 32x32 fp32 staging tile in shared memory (4 KB, float4 slots,
+// XOR-swizzled so both access patterns below are bank-conflict free).  tcgen05.ld hands a
+// thread one accumulator ROW (32 consecutive columns); global memory wants a warp to touch
+// one row segment per instruction.  The tile converts between the two, so every global
+// load/store of the epilogue is a full 128-byte (fp32) / 64-byte (bf16) row segment.
+__device__ __forceinline__ void tile_put_row(float4* st, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) st[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void tile_get_row(const float4* st, int lane, float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = st[lane * 8 + (j ^ (lane & 7))];
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+}
+// g points at (first row of this warp's 32-row group, first column of the chunk)
+__device__ __forceinline__ void tile_load_f32(float4* st, int lane, const float* g, int64_t ld, int rows_valid, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3), grp = lane & 7;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rows_valid) x = __ldg(reinterpret_cast<const float4*>(g + (int64_t)row * ld + 4 * grp));
+    st[row * 8 + (grp ^ (row & 7))] = x;
+  }
+  __syncwarp();
+  tile_get_row(st, lane, v);
+  __syncwarp();
+}
+__device__ __forceinline__ void tile_load_bf16(float4* st, int lane, const bf16* g, int64_t ld, int rows_valid, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + (lane >> 2), piece = lane & 3;
+    uint4 x = make_uint4(0, 0, 0, 0);
+    if (row < rows_valid) x = __ldg(reinterpret_cast<const uint4*>(g + (int64_t)row * ld + 8 * piece));
+    st[row * 8 + ((2 * piece) ^ (row & 7))] = make_float4(bf16lo(x.x), bf16hi(x.x), bf16lo(x.y), bf16hi(x.y));
+    st[row * 8 + ((2 * piece + 1) ^ (row & 7))] = make_float4(bf16lo(x.z), bf16hi(x.z), bf16lo(x.w), bf16hi(x.w));
+  }
+  __syncwarp();
+  tile_get_row(st, lane, v);
+  __syncwarp();
+}
+__device__ __forceinline__ void tile_store_f32(float4* st, int lane, float* g, int64_t ld, int rows_valid, const float (&v)[32]) {
+  tile_put_row(st, lane, v);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3), grp = lane & 7;
+    if (row < rows_valid) *reinterpret_cast<float4*>(g + (int64_t)row * ld + 4 * grp) = st[row * 8 + (grp ^ (row & 7))];
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void tile_store_bf16(float4* st, int lane, bf16* g, int64_t ld, int rows_valid, const float (&v)[32]) {
+  tile_put_row(st, lane, v);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + (lane >> 2), piece = lane & 3;
+    if (row < rows_valid) {
+      const float4 a = st[row * 8 + ((2 * piece) ^ (row & 7))];
+      const float4 c = st[row * 8 + ((2 * piece + 1) ^ (row & 7))];
+      *reinterpret_cast<uint4*>(g + (int64_t)row * ld + 8 * piece) =
+          make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y), pack_bf16(c.z, c.w));
+    }
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------ epilogue: one 32x32 chunk per warp
+// v: this thread's accumulator row (row = row0 + lane), columns [col0, col0+32).
+// Warp-uniform: col0, ncols, row0.  `full` = chunk fully inside N and 16-byte vector access legal.
+__device__ __forceinline__ void epilogue_linear(const GemmParams& p, float4* st, int lane, float (&v)[32], int row0,
+                                                int col0, int ncols, uint32_t drop_key) {
   const KmbGemmEpilogue& e = p.e;
   const bool full = (ncols == 32) && p.vec_ok;
+  const int row = row0 + lane;
+  const bool row_ok = row < p.M;
+  int rows_valid = p.M - row0;
+  rows_valid = rows_valid > 32 ? 32 : rows_valid;
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
   if (e.bias) {
@@ -89,17 +164,13 @@ __device__ __forceinline__ void epilogue_linear(const GemmParams& p, float (&v)[
   }
   if (e.act == KMB_ACT_GELU) {
     if (e.out_preact) {
-      bf16* pp = reinterpret_cast<bf16*>(e.out_preact) + (int64_t)row * e.ld_bf16 + col0;
+      bf16* pp = reinterpret_cast<bf16*>(e.out_preact) + (int64_t)row0 * e.ld_bf16 + col0;
       if (full) {
-        uint4* q = reinterpret_cast<uint4*>(pp);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          q[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-      } else {
+        tile_store_bf16(st, lane, pp, e.ld_bf16, rows_valid, v);
+      } else if (row_ok) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j < ncols) pp[j] = __float2bfloat16(v[j]);
+          if (j < ncols) pp[(int64_t)lane * e.ld_bf16 + j] = __float2bfloat16(v[j]);
       }
     }
 #pragma unroll
@@ -108,21 +179,13 @@ __device__ __forceinline__ void epilogue_linear(const GemmParams& p, float (&v)[
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
   } else if (e.act == KMB_ACT_GELU_GRAD || e.act == KMB_ACT_TANH_GRAD) {
-    const bf16* ap = reinterpret_cast<const bf16*>(e.aux) + (int64_t)row * e.ld_aux + col0;
+    const bf16* ap = reinterpret_cast<const bf16*>(e.aux) + (int64_t)row0 * e.ld_aux + col0;
     float a[32];
     if (full) {
-      const uint4* q = reinterpret_cast<const uint4*>(ap);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 t = __ldg(q + j);
-        a[8 * j] = bf16lo(t.x); a[8 * j + 1] = bf16hi(t.x);
-        a[8 * j + 2] = bf16lo(t.y); a[8 * j + 3] = bf16hi(t.y);
-        a[8 * j + 4] = bf16lo(t.z); a[8 * j + 5] = bf16hi(t.z);
-        a[8 * j + 6] = bf16lo(t.w); a[8 * j + 7] = bf16hi(t.w);
-      }
+      tile_load_bf16(st, lane, ap, e.ld_aux, rows_valid, a);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) a[j] = (j < ncols) ? __bfloat162float(ap[j]) : 0.f;
+      for (int j = 0; j < 32; ++j) a[j] = (row_ok && j < ncols) ? __bfloat162float(ap[(int64_t)lane * e.ld_aux + j]) : 0.f;
     }
     if (e.act == KMB_ACT_GELU_GRAD) {
 #pragma unroll
@@ -133,70 +196,62 @@ __device__ __forceinline__ void epilogue_linear(const GemmParams& p, float (&v)[
     }
   }
   if (p.drop_thresh16) {
-    const uint64_t base = (uint64_t)row * (uint64_t)p.N + (uint64_t)col0;  // col0 % 32 == 0
+    const uint64_t base = (uint64_t)row * (uint64_t)p.N + (uint64_t)col0;  // col0 % 32 == 0, N % 4 == 0
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const uint64_t bits = dropout_bits4(seed, e.dropout_tag, (base >> 2) + j);
+      const uint64_t bits = dropout_bits4_k(drop_key, (base >> 2) + j);
 #pragma unroll
       for (int l = 0; l < 4; ++l)
         v[4 * j + l] = dropout_keep(bits, l, p.drop_thresh16) ? v[4 * j + l] * p.drop_scale : 0.f;
     }
   }
   if (e.residual) {
-    const float* rp = e.residual + (int64_t)row * e.ld_res + col0;
+    const float* rp = e.residual + (int64_t)row0 * e.ld_res + col0;
     if (full) {
-      const float4* r4 = reinterpret_cast<const float4*>(rp);
+      float r[32];
+      tile_load_f32(st, lane, rp, e.ld_res, rows_valid, r);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 t = __ldg(r4 + j);
-        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-      }
-    } else {
+      for (int j = 0; j < 32; ++j) v[j] += r[j];
+    } else if (row_ok) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j < ncols) v[j] += rp[j];
+        if (j < ncols) v[j] += rp[(int64_t)lane * e.ld_res + j];
     }
   }
   if (e.out_f32) {
-    float* op = e.out_f32 + (int64_t)row * e.ld_f32 + col0;
+    float* op = e.out_f32 + (int64_t)row0 * e.ld_f32 + col0;
     if (full) {
-      float4* o4 = reinterpret_cast<float4*>(op);
       if (e.accumulate) {
+        float r[32];
+        tile_load_f32(st, lane, op, e.ld_f32, rows_valid, r);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 t = o4[j];
-          v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-        }
+        for (int j = 0; j < 32; ++j) v[j] += r[j];
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } else {
+      tile_store_f32(st, lane, op, e.ld_f32, rows_valid, v);
+    } else if (row_ok) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (j < ncols) {
-          if (e.accumulate) v[j] += op[j];
-          op[j] = v[j];
+          float* q = op + (int64_t)lane * e.ld_f32 + j;
+          if (e.accumulate) v[j] += *q;
+          *q = v[j];
         }
     }
   }
   if (e.out_bf16) {
-    bf16* op = reinterpret_cast<bf16*>(e.out_bf16) + (int64_t)row * e.ld_bf16 + col0;
+    bf16* op = reinterpret_cast<bf16*>(e.out_bf16) + (int64_t)row0 * e.ld_bf16 + col0;
     if (full) {
-      uint4* q = reinterpret_cast<uint4*>(op);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        q[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                          pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-    } else {
+      tile_store_bf16(st, lane, op, e.ld_bf16, rows_valid, v);
+    } else if (row_ok) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j < ncols) op[j] = __float2bfloat16(v[j]);
+        if (j < ncols) op[(int64_t)lane * e.ld_bf16 + j] = __float2bfloat16(v[j]);
     }
   }
 }
 
 template <int BN, int ELT, int A_MN, int B_MN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   using C = Cfg<BN>;
@@ -216,6 +271,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float4* stage_tiles = reinterpret_cast<float4*>(smem + STAGES * C::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -231,7 +287,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], 256);
     }
     fence_mbar_init();
   }
@@ -310,42 +366,51 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (8 warps) =====================
+    // warp w may only touch TMEM lanes [32*(w%4), +32); warps 4..7 take even 32-column chunks,
+    // warps 8..11 the odd ones.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    float4* st = stage_tiles + (warp - 4) * 256;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const uint64_t seed = (p.drop_thresh16 && p.e.dropout_seed) ? *p.e.dropout_seed : 0ull;
+    uint32_t drop_key = 0;
+    if (p.drop_thresh16 && p.e.dropout_seed) drop_key = dropout_key(*p.e.dropout_seed, p.e.dropout_tag);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
-      const int row = m_blk * BM + q * 32 + lane;
+      const int row0 = m_blk * BM + q * 32;
+      const int row = row0 + lane;
       const int n0 = n_blk * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
       const bool row_ok = row < p.M;
+      int rows_valid = p.M - row0;
+      rows_valid = rows_valid > 32 ? 32 : rows_valid;
 
       if (p.e.mode == KMB_EPI_LINEAR) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half; c < BN / 32; c += 2) {
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
           const int col0 = n0 + c * 32;
           int ncols = p.N - col0;
           ncols = ncols > 32 ? 32 : ncols;
-          if (row_ok && ncols > 0) {
+          if (rows_valid > 0 && ncols > 0) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            epilogue_linear<BN>(p, v, row, col0, ncols, seed);
+            epilogue_linear(p, st, lane, v, row0, col0, ncols, drop_key);
           }
         }
       } else if (p.e.mode == KMB_EPI_CE_STATS) {
-        // online softmax partial over this tile's columns (+ final_logits_bias)
+        // online softmax partial over this warp's columns of the tile (+ final_logits_bias);
+        // partial index = n_blk * 2 + half
         float mx = -INFINITY, sm = 0.f;
         const int64_t label = row_ok ? p.e.labels[row] : -100;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half; c < BN / 32; c += 2) {
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
@@ -380,23 +445,22 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (row_ok) {
-          p.e.ce_max[(int64_t)row * p.n_tiles + n_blk] = mx;
-          p.e.ce_sum[(int64_t)row * p.n_tiles + n_blk] = sm;
+          p.e.ce_max[(int64_t)row * (2 * p.n_tiles) + 2 * n_blk + half] = mx;
+          p.e.ce_sum[(int64_t)row * (2 * p.n_tiles) + 2 * n_blk + half] = sm;
         }
       } else {  // KMB_EPI_CE_GRAD
         const int64_t label = row_ok ? p.e.labels[row] : -100;
         const float lse = row_ok ? p.e.ce_lse[row] : 0.f;
         const float gs = (label >= 0) ? *p.e.ce_gscale : 0.f;
-        bf16* orow = reinterpret_cast<bf16*>(p.e.out_bf16) + (int64_t)row * p.e.ld_bf16;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half; c < BN / 32; c += 2) {
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
           const int col0 = n0 + c * 32;
           int ncols = p.N - col0;
           ncols = ncols > 32 ? 32 : ncols;
-          if (row_ok && ncols > 0) {
+          if (rows_valid > 0 && ncols > 0) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -406,16 +470,13 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (col0 + j == (int)label) pr -= 1.f;
               v[j] = pr * gs;
             }
+            bf16* og = reinterpret_cast<bf16*>(p.e.out_bf16) + (int64_t)row0 * p.e.ld_bf16 + col0;
             if (ncols == 32 && p.vec_ok) {
-              uint4* qd = reinterpret_cast<uint4*>(orow + col0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                qd[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-            } else {
+              tile_store_bf16(st, lane, og, p.e.ld_bf16, rows_valid, v);
+            } else if (row_ok) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j < ncols) orow[col0 + j] = __float2bfloat16(v[j]);
+                if (j < ncols) og[(int64_t)lane * p.e.ld_bf16 + j] = __float2bfloat16(v[j]);
             }
           }
         }
@@ -506,7 +567,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 256, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+  kern<<<grid, 384, C::SMEM_BYTES, st>>>(tmA, tmB, p);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }
@@ -549,9 +610,11 @@ extern "C" int kmb_gemm_pick_tile_n(int M, int N) {
   return best;
 }
 
+// number of (max, sumexp) partials per row that KMB_EPI_CE_STATS writes: two per n-tile
+// (one per epilogue column half)
 extern "C" int kmb_gemm_n_tiles(int N, int tile_n) {
   if (tile_n != 32 && tile_n != 64 && tile_n != 128 && tile_n != 256) return KMB_ERR_ARG;
-  return (N + tile_n - 1) / tile_n;
+  return 2 * ((N + tile_n - 1) / tile_n);
 }
 
 extern "C" int kmb_gemm(const void* A, const void* B, int M, int N, int K, int64_t lda, int64_t ldb,

@@ -280,80 +280,91 @@ struct LnBwdParams {
   DropCfg drop_in, drop_out;
 };
 
-template <int NV>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+// Column-owner layout: thread t owns the float4 column group t of every row the block visits, so
+// the dgamma / dbeta / dbias column sums are three float4 registers per thread (no big per-warp
+// accumulator arrays -> high occupancy), and a row is read by d/4 consecutive threads (coalesced).
+// Row statistics (mean of g, mean of g*xhat) are block-reduced for LN_RB rows at a time.
+constexpr int LN_RB = 4;
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p, int rows_per_block) {
   const int d = p.d;
-  float4 ag[NV], ab[NV], az[NV];
+  const int c = threadIdx.x * 4;
+  const bool active = c < d;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __shared__ float red[2][LN_RB][2][8];
+  const uint32_t key_in = p.drop_in.thresh16 ? dropout_key(*p.drop_in.seed, p.drop_in.tag) : 0u;
+  const uint32_t key_out = p.drop_out.thresh16 ? dropout_key(*p.drop_out.seed, p.drop_out.tag) : 0u;
+  float4 gm = make_float4(0, 0, 0, 0);
+  if (active) gm = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
+  float4 ag = make_float4(0, 0, 0, 0), ab = ag, az = ag;
+  const int r_begin = blockIdx.x * rows_per_block;
+  const int r_end = min(p.M, r_begin + rows_per_block);
+  int buf = 0;
+  for (int r0 = r_begin; r0 < r_end; r0 += LN_RB, buf ^= 1) {
+    float4 g[LN_RB], xh[LN_RB], dyv[LN_RB];
+    float rs[LN_RB];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = az[i] = make_float4(0, 0, 0, 0);
-  const uint64_t seed_in = p.drop_in.thresh16 ? *p.drop_in.seed : 0ull;
-  const uint64_t seed_out = p.drop_out.thresh16 ? *p.drop_out.seed : 0ull;
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < p.M; row += nwarps) {
-    const float mean = p.mean[row], rstd = p.rstd[row];
-    float4 g[NV], xh[NV];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < d) {
+    for (int i = 0; i < LN_RB; ++i) {
+      const int row = r0 + i;
+      g[i] = xh[i] = dyv[i] = make_float4(0, 0, 0, 0);
+      rs[i] = 0.f;
+      float s1 = 0.f, s2 = 0.f;
+      if (row < r_end && active) {
         float4 dy = *reinterpret_cast<const float4*>(p.dy + (int64_t)row * d + c);
-        if (p.drop_in.thresh16) dy = drop4(dy, seed_in, p.drop_in, ((uint64_t)row * d + c) >> 2);
+        if (p.drop_in.thresh16) {
+          const uint64_t bits = dropout_bits4_k(key_in, ((uint64_t)row * d + c) >> 2);
+          dy.x = dropout_keep(bits, 0, p.drop_in.thresh16) ? dy.x * p.drop_in.scale : 0.f;
+          dy.y = dropout_keep(bits, 1, p.drop_in.thresh16) ? dy.y * p.drop_in.scale : 0.f;
+          dy.z = dropout_keep(bits, 2, p.drop_in.thresh16) ? dy.z * p.drop_in.scale : 0.f;
+          dy.w = dropout_keep(bits, 3, p.drop_in.thresh16) ? dy.w * p.drop_in.scale : 0.f;
+        }
         const float4 x = *reinterpret_cast<const float4*>(p.pre + (int64_t)row * d + c);
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
+        const float mean = __ldg(p.mean + row), rstd = __ldg(p.rstd + row);
+        rs[i] = rstd;
+        dyv[i] = dy;
         xh[i] = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
         g[i] = make_float4(dy.x * gm.x, dy.y * gm.y, dy.z * gm.z, dy.w * gm.w);
-        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
-        s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
-        ag[i].x += dy.x * xh[i].x; ag[i].y += dy.y * xh[i].y; ag[i].z += dy.z * xh[i].z; ag[i].w += dy.w * xh[i].w;
-        ab[i].x += dy.x; ab[i].y += dy.y; ab[i].z += dy.z; ab[i].w += dy.w;
+        s1 = g[i].x + g[i].y + g[i].z + g[i].w;
+        s2 = g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
       }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) { red[buf][i][0][wib] = s1; red[buf][i][1][wib] = s2; }
     }
-    s1 = warp_sum(s1) / d;
-    s2 = warp_sum(s2) / d;
+    __syncthreads();
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < d) {
+    for (int i = 0; i < LN_RB; ++i) {
+      const int row = r0 + i;
+      if (row < r_end && active) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int w = 0; w < nw; ++w) { s1 += red[buf][i][0][w]; s2 += red[buf][i][1][w]; }
+        s1 /= d; s2 /= d;
         float4 dx;
-        dx.x = rstd * (g[i].x - s1 - xh[i].x * s2);
-        dx.y = rstd * (g[i].y - s1 - xh[i].y * s2);
-        dx.z = rstd * (g[i].z - s1 - xh[i].z * s2);
-        dx.w = rstd * (g[i].w - s1 - xh[i].w * s2);
+        dx.x = rs[i] * (g[i].x - s1 - xh[i].x * s2);
+        dx.y = rs[i] * (g[i].y - s1 - xh[i].y * s2);
+        dx.z = rs[i] * (g[i].z - s1 - xh[i].z * s2);
+        dx.w = rs[i] * (g[i].w - s1 - xh[i].w * s2);
         if (p.dpre) *reinterpret_cast<float4*>(p.dpre + (int64_t)row * d + c) = dx;
+        ag.x += dyv[i].x * xh[i].x; ag.y += dyv[i].y * xh[i].y; ag.z += dyv[i].z * xh[i].z; ag.w += dyv[i].w * xh[i].w;
+        ab.x += dyv[i].x; ab.y += dyv[i].y; ab.z += dyv[i].z; ab.w += dyv[i].w;
         if (p.dz || p.dbias) {
           float4 z = dx;
-          if (p.drop_out.thresh16) z = drop4(z, seed_out, p.drop_out, ((uint64_t)row * d + c) >> 2);
+          if (p.drop_out.thresh16) {
+            const uint64_t bits = dropout_bits4_k(key_out, ((uint64_t)row * d + c) >> 2);
+            z.x = dropout_keep(bits, 0, p.drop_out.thresh16) ? z.x * p.drop_out.scale : 0.f;
+            z.y = dropout_keep(bits, 1, p.drop_out.thresh16) ? z.y * p.drop_out.scale : 0.f;
+            z.z = dropout_keep(bits, 2, p.drop_out.thresh16) ? z.z * p.drop_out.scale : 0.f;
+            z.w = dropout_keep(bits, 3, p.drop_out.thresh16) ? z.w * p.drop_out.scale : 0.f;
+          }
           if (p.dz) *reinterpret_cast<uint2*>(p.dz + (int64_t)row * d + c) = pack4(z);
-          az[i].x += z.x; az[i].y += z.y; az[i].z += z.z; az[i].w += z.w;
+          az.x += z.x; az.y += z.y; az.z += z.z; az.w += z.w;
         }
       }
     }
   }
-  // block-level column reduction through shared memory, then one atomic per column per block
-  __shared__ float4 red[8][32];
-  for (int which = 0; which < 3; ++which) {
-    float* dst = which == 0 ? p.dgamma : (which == 1 ? p.dbeta : p.dbias);
-    if (!dst) continue;  // uniform across the block
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float4 v = which == 0 ? ag[i] : (which == 1 ? ab[i] : az[i]);
-      red[wib][lane] = v;
-      __syncthreads();
-      if (wib == 0) {
-        float4 t = red[0][lane];
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
-          const float4 u = red[w][lane];
-          t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
-        }
-        const int c = (i * 32 + lane) * 4;
-        if (c < d) {
-          atomicAdd(dst + c, t.x); atomicAdd(dst + c + 1, t.y); atomicAdd(dst + c + 2, t.z); atomicAdd(dst + c + 3, t.w);
-        }
-      }
-      __syncthreads();
-    }
+  if (active) {
+    if (p.dgamma) { atomicAdd(p.dgamma + c, ag.x); atomicAdd(p.dgamma + c + 1, ag.y); atomicAdd(p.dgamma + c + 2, ag.z); atomicAdd(p.dgamma + c + 3, ag.w); }
+    if (p.dbeta) { atomicAdd(p.dbeta + c, ab.x); atomicAdd(p.dbeta + c + 1, ab.y); atomicAdd(p.dbeta + c + 2, ab.z); atomicAdd(p.dbeta + c + 3, ab.w); }
+    if (p.dbias) { atomicAdd(p.dbias + c, az.x); atomicAdd(p.dbias + c + 1, az.y); atomicAdd(p.dbias + c + 2, az.z); atomicAdd(p.dbias + c + 3, az.w); }
   }
 }
 
@@ -544,10 +555,17 @@ extern "C" int kmb_layernorm_bwd(const float* dy, const float* pre, const float*
   p.dgamma = dgamma; p.dbeta = dbeta; p.dbias = dbias; p.M = M; p.d = d;
   p.drop_in = make_drop(drop_in_p, drop_in_tag, dropout_seed);
   p.drop_out = make_drop(drop_out_p, drop_out_tag, dropout_seed);
-  int blocks = (M + 7) / 8;
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  cudaStream_t st = (cudaStream_t)stream;
-  KMB_DISPATCH_NV(d, (ln_bwd_kernel<6><<<blocks, 256, 0, st>>>(p)), (ln_bwd_kernel<8><<<blocks, 256, 0, st>>>(p)));
+  if ((d % 4) || d > 1024) {
+    kmb_set_last_error("kmb_layernorm_bwd: d_model must be a multiple of 4 and <= 1024", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  // ~148 SMs x 8 resident blocks; at least LN_RB rows per block so the statistics batch is full
+  int rows_per_block = (M + 148 * 8 - 1) / (148 * 8);
+  rows_per_block = (rows_per_block + LN_RB - 1) / LN_RB * LN_RB;
+  if (rows_per_block < 2 * LN_RB) rows_per_block = 2 * LN_RB;
+  const int blocks = (M + rows_per_block - 1) / rows_per_block;
+  const int threads = ((d / 4) + 31) / 32 * 32;
+  ln_bwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(p, rows_per_block);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }

@@ -478,13 +478,12 @@ class Engine:
                   accumulate=0 if first_cross else 1)
         self.gemm(plan, dq2, st.p16(lp + ".encoder_attn.q_proj.weight"), Md, d, d, d, d, b_mn=1, residual=dpre, out_f32=dres_out)
 
-    def _build_train_plans(self, a, key):
-        cfg, st, d, V = self.cfg, self.store, self.cfg.d_model, self.cfg.vocab_size
+    def _build_train_fwd(self, a):
+        cfg = self.cfg
         B, Se, Sd, R = a["B"], a["Se"], a["Sd"], a["R"]
         Me, Md = B * Se, B * Sd
         a["Me"], a["Md"] = Me, Md
         p_drop = float(cfg.dropout) if a["training"] else 0.0
-        acc = int(a["accumulate"])
         assert float(cfg.attention_dropout) == 0.0 or not a["training"], "attention_dropout > 0 is not supported"
         assert float(cfg.activation_dropout) == 0.0 or not a["training"], "activation_dropout > 0 is not supported"
         fwd = Plan()
@@ -494,7 +493,16 @@ class Engine:
         _, enc_b16 = self._encoder_fwd(fwd, a, B, Se, R, True, p_drop)
         self._decoder_fwd(fwd, a, B, Sd, Se, True, p_drop, enc_b16)
         self._lm_loss_fwd(fwd, a, Md, a["lm_factor"], add_total=False)
+        return fwd
 
+    def _build_train_bwd(self, a, acc):
+        """acc = 1: gradients are added onto the flat gradient buffer (gradient accumulation /
+        zero_grad(set_to_none=False)); acc = 0: the buffer is overwritten."""
+        cfg, st, d, V = self.cfg, self.store, self.cfg.d_model, self.cfg.vocab_size
+        B, Se, Sd, R = a["B"], a["Se"], a["Sd"], a["R"]
+        Me, Md = B * Se, B * Sd
+        p_drop = float(cfg.dropout) if a["training"] else 0.0
+        acc = int(acc)
         bwd = Plan()
         bwd.stream = a["stream"]
         if not acc:
@@ -556,7 +564,7 @@ class Engine:
             self.gemm(bwd, dvis, a["feats16"], d, self.fin - 4, R, d, self.fin - 4, a_mn=1, b_mn=1, out_f32=st.g(wname),
                       ld_f32=self.fin, accumulate=acc)
             bwd.add(self.lib.kmb_box_wgrad, _ptr(dvis), _ptr(a["boxes"]), _ptr(st.g(wname)), R, d, self.fin, bwd.stream)
-        return fwd, bwd
+        return bwd
 
     # ------------------------------------------------------------------ input staging
     def _stage_inputs(self, a, input_ids, image_features, attention_mask, decoder_input_ids, decoder_attention_mask, labels):
@@ -580,7 +588,7 @@ class Engine:
             a["feat_ptrs"].copy_(a["feat_ptrs_host"], non_blocking=True)
         a["row_off"].copy_(a["row_off_host"], non_blocking=True)
 
-    def _get_arena(self, mode, input_ids, image_features, attention_mask, decoder_input_ids, labels, training, accumulate,
+    def _get_arena(self, mode, input_ids, image_features, attention_mask, decoder_input_ids, labels, training,
                    lm_factor=1.0, image_counts=None):
         B, Se = input_ids.shape
         Sd = decoder_input_ids.shape[1] if decoder_input_ids is not None else 0
@@ -597,11 +605,11 @@ class Engine:
                         "image_features must be CUDA fp32 [n_i, 2052] tensors"
         R = sum(counts)
         stream = self.stream()
-        key = (mode, B, Se, Sd, R, attention_mask is not None, bool(training), bool(accumulate), packed, float(lm_factor), stream)
+        key = (mode, B, Se, Sd, R, attention_mask is not None, bool(training), packed, float(lm_factor), stream)
         a = self.arenas.get(key)
         if a is None:
             dev = self.device
-            a = {"__dev": dev, "B": B, "Se": Se, "Sd": Sd, "R": R, "training": bool(training), "accumulate": bool(accumulate),
+            a = {"__dev": dev, "B": B, "Se": Se, "Sd": Sd, "R": R, "training": bool(training),
                  "has_mask_e": attention_mask is not None, "stream": stream, "lm_factor": float(lm_factor)}
             a["ids_e"] = torch.empty(B * Se, dtype=torch.int64, device=dev)
             a["amask_e"] = torch.empty(B * Se, dtype=torch.int64, device=dev)
@@ -627,30 +635,38 @@ class Engine:
 
     # ------------------------------------------------------------------ public: training step pieces
     def train_forward(self, input_ids, image_features, attention_mask, decoder_input_ids, decoder_attention_mask, labels,
-                      final_logits_bias, training, accumulate=False, lm_factor=1.0, image_counts=None):
+                      final_logits_bias, training, lm_factor=1.0, image_counts=None):
         self.sync_shadow()
         a, key = self._get_arena("train", input_ids, image_features, attention_mask, decoder_input_ids, labels, training,
-                                 accumulate, lm_factor, image_counts)
+                                 lm_factor, image_counts)
         a["flb"] = final_logits_bias.reshape(-1)
         self._stage_inputs(a, input_ids, image_features, attention_mask, decoder_input_ids, decoder_attention_mask, labels)
         plans = self.plans.get(key)
-        if plans is None or plans[2] != a["flb"].data_ptr():
-            fwd, bwd = self._build_train_plans(a, key)
-            plans = (fwd, bwd, a["flb"].data_ptr())
+        if plans is None or plans["flb"] != a["flb"].data_ptr():
+            plans = {"fwd": self._build_train_fwd(a), "flb": a["flb"].data_ptr()}
             self.plans[key] = plans
-        plans[0].run()
+        plans["fwd"].run()
         self.last_train = (a, key)
-        self.launches_last = len(plans[0])
+        self.launches_last = len(plans["fwd"])
         return a
 
-    def train_backward(self, a, key, upstream):
+    def grads_alias_flat_buffer(self):
+        """True when existing .grad tensors still live in the flat gradient buffer (gradient
+        accumulation, or zero_grad(set_to_none=False)): the backward must then add in place."""
+        base, end = self.store.G.data_ptr(), self.store.G.data_ptr() + 4 * self.store.total
+        return any(p.grad is not None and base <= p.grad.data_ptr() < end for p in self.store.params.values())
+
+    def train_backward(self, a, key, upstream, accumulate):
         if upstream is not None:
             self.upstream.copy_(upstream.reshape(1).to(F32))
         else:
             self.upstream.fill_(1.0)
         plans = self.plans[key]
-        plans[1].run()
-        self.launches_last += len(plans[1])
+        name = "bwd1" if accumulate else "bwd0"
+        if name not in plans:
+            plans[name] = self._build_train_bwd(a, accumulate)
+        plans[name].run()
+        self.launches_last += len(plans[name])
 
     # ------------------------------------------------------------------ public: inference forward (no cache)
     def infer_forward(self, input_ids, image_features, attention_mask, decoder_input_ids, decoder_attention_mask,
@@ -658,7 +674,7 @@ class Engine:
         """Full-sequence forward without stashing; returns (enc_f32 [B,Se,d], dec_f32 [B,Sd,d] or None, arena)."""
         self.sync_shadow()
         a, key = self._get_arena("enc" if encoder_only else "infer", input_ids, image_features, attention_mask,
-                                 None if encoder_only else decoder_input_ids, None, False, False, 1.0, image_counts)
+                                 None if encoder_only else decoder_input_ids, None, False, 1.0, image_counts)
         self._stage_inputs(a, input_ids, image_features, attention_mask, None if encoder_only else decoder_input_ids,
                            decoder_attention_mask, None)
         plan = self.plans.get(key)

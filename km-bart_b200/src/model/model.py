@@ -76,10 +76,13 @@ class _FusedTrainStep(torch.autograd.Function):
     def backward(ctx, grad_loss):
         owner = ctx.owner
         eng = owner._engine()
-        eng.train_backward(ctx.arena, ctx.key, grad_loss)
+        # decided here, not at forward time: the reference's loop calls optimizer.zero_grad() between
+        # forward and backward (src/training.py:134-142)
+        accumulate = eng.grads_alias_flat_buffer()
+        eng.train_backward(ctx.arena, ctx.key, grad_loss, accumulate)
         store = eng.store
-        if ctx.arena["accumulate"]:
-            # gradients were accumulated in place into the buffer the existing .grad tensors alias
+        if accumulate:
+            # gradients were added in place into the buffer the existing .grad tensors alias
             return (None, None, None) + (None,) * ctx.n_params
         grads = []
         for name, p in owner._named_params_cache:
@@ -257,16 +260,8 @@ class _LMBase(FromPretrainedMixin, GenerationMixin, PretrainedBartModel):
         if decoder_input_ids is None:
             decoder_input_ids = _shift_tokens_right(input_ids, cfg.pad_token_id)
         grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        accumulate = False
-        if grad:
-            base, end = eng.store.G.data_ptr(), eng.store.G.data_ptr() + 4 * eng.store.total
-            aliased = [p.grad is not None and base <= p.grad.data_ptr() < end for p in self.parameters()]
-            if any(aliased):
-                # .grad tensors still alias the flat buffer (zero_grad(set_to_none=False) or gradient
-                # accumulation): accumulate in place and return nothing new for those
-                accumulate = True
         a = eng.train_forward(input_ids, image_features, attention_mask, decoder_input_ids, decoder_attention_mask, labels,
-                              self.final_logits_bias, self.training, accumulate=accumulate, lm_factor=lm_factor)
+                              self.final_logits_bias, self.training, lm_factor=lm_factor)
         key = eng.last_train[1]
         if grad:
             params = [p for _, p in self._named_params_cache]

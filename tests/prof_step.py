@@ -31,3 +31,7 @@ for _ in range(steps):
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
 print("done")
+print("opt.launches_last", opt.launches_last, "eng.launches_last", model._engine().launches_last)
+print("n params with grad", sum(p.grad is not None for p in model.parameters()))
+st = opt.state[next(iter(model.parameters()))]
+print("state step", st.get("step"), "exp_avg norm", st["exp_avg"].norm().item() if "exp_avg" in st else None)
