@@ -158,12 +158,16 @@ int kmb_box_wgrad(const void* dvis_bf16, const float* boxes, float* dw_img, int 
  * LayerNorm (eps 1e-5) on the fp32 residual stream.
  * replaces: HF-3.0.2 LayerNorm = torch.nn.LayerNorm in EncoderLayer/DecoderLayer (post-LN,
  *   normalize_before=False) and layernorm_embedding (src/model/modules.py:85,136).
- * bwd also produces dz = dropout-re-masked bf16 copy of dpre (the dY operand of the Linear
- * that fed the residual add) and accumulates dgamma/dbeta/dbias column sums.
+ * fwd fuses the residual add and the dropout that sit between a sublayer's last Linear and its
+ * LayerNorm: pre = residual + dropout(z), y = LN(pre); z = NULL gives a plain LN of `residual`.
+ * bwd takes the incoming gradient as an fp32 part (residual path) plus an optional bf16 part
+ * (dgrad GEMM output), produces dpre, dz = dropout-re-masked bf16 copy of dpre (the dY operand
+ * of the Linear that fed the residual add) and accumulates dgamma/dbeta/dbias column sums.
  */
-int kmb_layernorm_fwd(const float* pre, const float* gamma, const float* beta, float* out_f32,
-                      void* out_bf16, float* mean, float* rstd, int M, int d, kmb_stream_t stream);
-int kmb_layernorm_bwd(const float* dy, const float* pre, const float* mean, const float* rstd,
+int kmb_layernorm_fwd(const void* z_bf16, const float* residual, const float* gamma, const float* beta,
+                      float* pre, float* out_f32, void* out_bf16, float* mean, float* rstd, int M, int d,
+                      float dropout_p, uint32_t dropout_tag, const uint64_t* dropout_seed, kmb_stream_t stream);
+int kmb_layernorm_bwd(const float* dy, const void* dy_bf16, const float* pre, const float* mean, const float* rstd,
                       const float* gamma, float* dpre, void* dz_bf16, float* dgamma, float* dbeta,
                       float* dbias, int M, int d, float drop_in_p, uint32_t drop_in_tag, float drop_out_p,
                       uint32_t drop_out_tag, const uint64_t* dropout_seed, kmb_stream_t stream);

@@ -209,20 +209,52 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const EmbedParams p) 
   }
 }
 
-// ------------------------------------------------------------------ LayerNorm forward
+// ------------------------------------------------------------------ residual + dropout + LayerNorm forward
+// pre = residual + dropout(z)   (z = bf16 output of the preceding Linear, bias included)
+// y   = LN(pre)                 written as fp32 (residual stream) and bf16 (next GEMM operand)
+// With z == nullptr the kernel is a plain LayerNorm of `pre_in`.
+// HF-3.0.2 EncoderLayer/DecoderLayer: x = LN(residual + F.dropout(sublayer(x))).
+struct LnFwdParams {
+  const bf16* z;          // [M, d] or null
+  const float* residual;  // [M, d] (or the LN input itself when z is null)
+  const float* gamma;
+  const float* beta;
+  float* pre;             // [M, d] fp32 LN input, stored for backward (may be null)
+  float* out_f32;
+  bf16* out_bf16;
+  float* mean;
+  float* rstd;
+  int M, d;
+  DropCfg drop;
+};
+
 template <int NV>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, float* out_f32, bf16* out_bf16,
-                                                     float* mean_o, float* rstd_o, int M, int d) {
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdParams p) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (row >= M) return;
+  if (row >= p.M) return;
+  const int d = p.d;
   float4 x[NV];
   float sum = 0.f;
+  const uint32_t key = p.drop.thresh16 ? dropout_key(*p.drop.seed, p.drop.tag) : 0u;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < d) {
-      x[i] = *reinterpret_cast<const float4*>(pre + (int64_t)row * d + c);
+      x[i] = *reinterpret_cast<const float4*>(p.residual + (int64_t)row * d + c);
+      if (p.z) {
+        const uint2 zz = *reinterpret_cast<const uint2*>(p.z + (int64_t)row * d + c);
+        float4 zv = make_float4(__uint_as_float(zz.x << 16), __uint_as_float(zz.x & 0xFFFF0000u),
+                                __uint_as_float(zz.y << 16), __uint_as_float(zz.y & 0xFFFF0000u));
+        if (p.drop.thresh16) {
+          const uint64_t bits = dropout_bits4_k(key, ((uint64_t)row * d + c) >> 2);
+          zv.x = dropout_keep(bits, 0, p.drop.thresh16) ? zv.x * p.drop.scale : 0.f;
+          zv.y = dropout_keep(bits, 1, p.drop.thresh16) ? zv.y * p.drop.scale : 0.f;
+          zv.z = dropout_keep(bits, 2, p.drop.thresh16) ? zv.z * p.drop.scale : 0.f;
+          zv.w = dropout_keep(bits, 3, p.drop.thresh16) ? zv.w * p.drop.scale : 0.f;
+        }
+        x[i].x += zv.x; x[i].y += zv.y; x[i].z += zv.z; x[i].w += zv.w;
+        if (p.pre) *reinterpret_cast<float4*>(p.pre + (int64_t)row * d + c) = x[i];
+      }
       sum += x[i].x + x[i].y + x[i].z + x[i].w;
     }
   }
@@ -238,22 +270,22 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ p
   }
   const float rstd = rsqrtf(warp_sum(var) / d + 1e-5f);
   if (lane == 0) {
-    if (mean_o) mean_o[row] = mean;
-    if (rstd_o) rstd_o[row] = rstd;
+    if (p.mean) p.mean[row] = mean;
+    if (p.rstd) p.rstd[row] = rstd;
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < d) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta + c));
       float4 y;
       y.x = (x[i].x - mean) * rstd * g.x + b.x;
       y.y = (x[i].y - mean) * rstd * g.y + b.y;
       y.z = (x[i].z - mean) * rstd * g.z + b.z;
       y.w = (x[i].w - mean) * rstd * g.w + b.w;
-      if (out_f32) *reinterpret_cast<float4*>(out_f32 + (int64_t)row * d + c) = y;
-      if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + (int64_t)row * d + c) = pack4(y);
+      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (int64_t)row * d + c) = y;
+      if (p.out_bf16) *reinterpret_cast<uint2*>(p.out_bf16 + (int64_t)row * d + c) = pack4(y);
     }
   }
 }
@@ -266,7 +298,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ p
 //       Linear and the residual add) — the dY operand of that Linear's dgrad / wgrad GEMMs.
 // dgamma/dbeta/dbias (+=): column sums of dy*xhat, dy, dz.  Zero them before the first call.
 struct LnBwdParams {
-  const float* dy;
+  const float* dy;    // fp32 part of the incoming gradient (residual path) or null
+  const bf16* dy_b;   // bf16 part (dgrad GEMM output of the consumer Linear) or null
   const float* pre;
   const float* mean;
   const float* rstd;
@@ -309,7 +342,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p, int ro
       rs[i] = 0.f;
       float s1 = 0.f, s2 = 0.f;
       if (row < r_end && active) {
-        float4 dy = *reinterpret_cast<const float4*>(p.dy + (int64_t)row * d + c);
+        float4 dy = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.dy) dy = *reinterpret_cast<const float4*>(p.dy + (int64_t)row * d + c);
+        if (p.dy_b) {
+          const uint2 t = *reinterpret_cast<const uint2*>(p.dy_b + (int64_t)row * d + c);
+          dy.x += __uint_as_float(t.x << 16); dy.y += __uint_as_float(t.x & 0xFFFF0000u);
+          dy.z += __uint_as_float(t.y << 16); dy.w += __uint_as_float(t.y & 0xFFFF0000u);
+        }
         if (p.drop_in.thresh16) {
           const uint64_t bits = dropout_bits4_k(key_in, ((uint64_t)row * d + c) >> 2);
           dy.x = dropout_keep(bits, 0, p.drop_in.thresh16) ? dy.x * p.drop_in.scale : 0.f;
@@ -528,30 +567,34 @@ extern "C" int kmb_embed_ln_fwd(const int64_t* ids, const int* slot_idx, const f
   return KMB_OK;
 }
 
-extern "C" int kmb_layernorm_fwd(const float* pre, const float* gamma, const float* beta, float* out_f32,
-                                 void* out_bf16, float* mean, float* rstd, int M, int d, kmb_stream_t stream) {
-  if (!pre || !gamma || !beta || M <= 0) {
+extern "C" int kmb_layernorm_fwd(const void* z_bf16, const float* residual, const float* gamma, const float* beta,
+                                 float* pre, float* out_f32, void* out_bf16, float* mean, float* rstd, int M, int d,
+                                 float dropout_p, uint32_t dropout_tag, const uint64_t* dropout_seed, kmb_stream_t stream) {
+  if (!residual || !gamma || !beta || M <= 0) {
     kmb_set_last_error("kmb_layernorm_fwd: bad argument", __FILE__, __LINE__);
     return KMB_ERR_ARG;
   }
+  LnFwdParams p;
+  p.z = (const bf16*)z_bf16; p.residual = residual; p.gamma = gamma; p.beta = beta; p.pre = pre; p.out_f32 = out_f32;
+  p.out_bf16 = (bf16*)out_bf16; p.mean = mean; p.rstd = rstd; p.M = M; p.d = d;
+  p.drop = make_drop(z_bf16 ? dropout_p : 0.f, dropout_tag, dropout_seed);
   const int blocks = (M * 32 + 255) / 256;
   cudaStream_t st = (cudaStream_t)stream;
-  KMB_DISPATCH_NV(d, (ln_fwd_kernel<6><<<blocks, 256, 0, st>>>(pre, gamma, beta, out_f32, (bf16*)out_bf16, mean, rstd, M, d)),
-                  (ln_fwd_kernel<8><<<blocks, 256, 0, st>>>(pre, gamma, beta, out_f32, (bf16*)out_bf16, mean, rstd, M, d)));
+  KMB_DISPATCH_NV(d, (ln_fwd_kernel<6><<<blocks, 256, 0, st>>>(p)), (ln_fwd_kernel<8><<<blocks, 256, 0, st>>>(p)));
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }
 
-extern "C" int kmb_layernorm_bwd(const float* dy, const float* pre, const float* mean, const float* rstd,
+extern "C" int kmb_layernorm_bwd(const float* dy, const void* dy_bf16, const float* pre, const float* mean, const float* rstd,
                                  const float* gamma, float* dpre, void* dz_bf16, float* dgamma, float* dbeta,
                                  float* dbias, int M, int d, float drop_in_p, uint32_t drop_in_tag, float drop_out_p,
                                  uint32_t drop_out_tag, const uint64_t* dropout_seed, kmb_stream_t stream) {
-  if (!dy || !pre || !mean || !rstd || !gamma || M <= 0) {
+  if ((!dy && !dy_bf16) || !pre || !mean || !rstd || !gamma || M <= 0) {
     kmb_set_last_error("kmb_layernorm_bwd: bad argument", __FILE__, __LINE__);
     return KMB_ERR_ARG;
   }
   LnBwdParams p;
-  p.dy = dy; p.pre = pre; p.mean = mean; p.rstd = rstd; p.gamma = gamma; p.dpre = dpre; p.dz = (bf16*)dz_bf16;
+  p.dy = dy; p.dy_b = (const bf16*)dy_bf16; p.pre = pre; p.mean = mean; p.rstd = rstd; p.gamma = gamma; p.dpre = dpre; p.dz = (bf16*)dz_bf16;
   p.dgamma = dgamma; p.dbeta = dbeta; p.dbias = dbias; p.M = M; p.d = d;
   p.drop_in = make_drop(drop_in_p, drop_in_tag, dropout_seed);
   p.drop_out = make_drop(drop_out_p, drop_out_tag, dropout_seed);

@@ -249,16 +249,19 @@ class Engine:
         plan.add(self.lib.kmb_gemm, _ptr(A), _ptr(B), M, N, K, lda, ldb, a_mn, b_mn, elt, C.byref(e), tile_n,
                  plan.stream, keep=e)
 
-    def ln_fwd(self, plan, pre, gname, out_f32, out_b16, mean, rstd, M):
+    def ln_fwd(self, plan, z_b16, residual, gname, pre, out_f32, out_b16, mean, rstd, M, drop=(0.0, 0)):
+        """y = LN(residual + dropout(z)); z None -> plain LN(residual)."""
         st, d = self.store, self.cfg.d_model
-        plan.add(self.lib.kmb_layernorm_fwd, _ptr(pre), _ptr(st.p32(gname + ".weight")), _ptr(st.p32(gname + ".bias")),
-                 _ptr(out_f32), _ptr(out_b16), _ptr(mean), _ptr(rstd), M, d, plan.stream)
+        plan.add(self.lib.kmb_layernorm_fwd, _ptr(z_b16), _ptr(residual), _ptr(st.p32(gname + ".weight")),
+                 _ptr(st.p32(gname + ".bias")), _ptr(pre), _ptr(out_f32), _ptr(out_b16), _ptr(mean), _ptr(rstd), M, d,
+                 drop[0], drop[1], self.seed.data_ptr(), plan.stream)
 
-    def ln_bwd(self, plan, dy, pre, mean, rstd, gname, dpre, dz, dbias, M, drop_in=(0.0, 0), drop_out=(0.0, 0)):
+    def ln_bwd(self, plan, dyA, dyB, pre, mean, rstd, gname, dpre, dz, dbias, M, drop_in=(0.0, 0), drop_out=(0.0, 0)):
         st, d = self.store, self.cfg.d_model
-        plan.add(self.lib.kmb_layernorm_bwd, _ptr(dy), _ptr(pre), _ptr(mean), _ptr(rstd), _ptr(st.p32(gname + ".weight")),
-                 _ptr(dpre), _ptr(dz), _ptr(st.g(gname + ".weight")), _ptr(st.g(gname + ".bias")), _ptr(dbias), M, d,
-                 drop_in[0], drop_in[1], drop_out[0], drop_out[1], self.seed.data_ptr(), plan.stream)
+        plan.add(self.lib.kmb_layernorm_bwd, _ptr(dyA), _ptr(dyB), _ptr(pre), _ptr(mean), _ptr(rstd),
+                 _ptr(st.p32(gname + ".weight")), _ptr(dpre), _ptr(dz), _ptr(st.g(gname + ".weight")),
+                 _ptr(st.g(gname + ".bias")), _ptr(dbias), M, d, drop_in[0], drop_in[1], drop_out[0], drop_out[1],
+                 self.seed.data_ptr(), plan.stream)
 
     def attn_fwd(self, plan, q, k, v, ldq, ldk, ldv, o, lse, pad, B, H, Sq, Sk, causal):
         plan.add(self.lib.kmb_attn_fwd, _ptr(q), _ptr(k), _ptr(v), ldq, ldk, ldv, _ptr(o), self.cfg.d_model, _ptr(lse),
@@ -288,10 +291,10 @@ class Engine:
         self.gemm(plan, x_b16, st.p16(lp + ".self_attn.q_proj.weight", 3 * d), M, 3 * d, d, d, d,
                   bias=st.fused32(lp + ".self_attn.q_proj.bias", 3), out_bf16=qkv)
         self.attn_fwd(plan, qkv, qkv[:, d:], qkv[:, 2 * d:], 3 * d, 3 * d, 3 * d, ctx, lse, pad, B, H, S, S, causal)
+        z = self.buf(a, f"zbuf{M}", (M, d), BF16)
         self.gemm(plan, ctx, st.p16(lp + ".self_attn.out_proj.weight"), M, d, d, d, d,
-                  bias=st.p32(lp + ".self_attn.out_proj.bias"), residual=x_f32, out_f32=pre,
-                  dropout_p=p_drop, dropout_tag=drop_tag)
-        self.ln_fwd(plan, pre, lp + ".self_attn_layer_norm", y_f32, y_b16, mean, rstd, M)
+                  bias=st.p32(lp + ".self_attn.out_proj.bias"), out_bf16=z)
+        self.ln_fwd(plan, z, x_f32, lp + ".self_attn_layer_norm", pre, y_f32, y_b16, mean, rstd, M, drop=(p_drop, drop_tag))
         return y_f32, y_b16
 
     def _ffn_block_fwd(self, plan, a, tag, lp, x_f32, x_b16, M, F, p_drop, drop_tag, train):
@@ -305,9 +308,9 @@ class Engine:
         rstd = self.buf(a, tag + "rstd3", (M,), F32)
         self.gemm(plan, x_b16, st.p16(lp + ".fc1.weight"), M, F, d, d, d, bias=st.p32(lp + ".fc1.bias"),
                   act=L.ACT_GELU, out_bf16=h, out_preact=u)
-        self.gemm(plan, h, st.p16(lp + ".fc2.weight"), M, d, F, F, F, bias=st.p32(lp + ".fc2.bias"),
-                  residual=x_f32, out_f32=pre, dropout_p=p_drop, dropout_tag=drop_tag)
-        self.ln_fwd(plan, pre, lp + ".final_layer_norm", y_f32, y_b16, mean, rstd, M)
+        z = self.buf(a, f"zbuf{M}", (M, d), BF16)
+        self.gemm(plan, h, st.p16(lp + ".fc2.weight"), M, d, F, F, F, bias=st.p32(lp + ".fc2.bias"), out_bf16=z)
+        self.ln_fwd(plan, z, x_f32, lp + ".final_layer_norm", pre, y_f32, y_b16, mean, rstd, M, drop=(p_drop, drop_tag))
         return y_f32, y_b16
 
     def _cross_block_fwd(self, plan, a, tag, lp, x_f32, x_b16, enc_b16, Md, Me, B, Sd, Se, H, pad_e, p_drop, drop_tag, train):
@@ -326,10 +329,10 @@ class Engine:
         self.gemm(plan, enc_b16, st.p16(lp + ".encoder_attn.k_proj.weight", 2 * d), Me, 2 * d, d, d, d,
                   bias=st.fused32(lp + ".encoder_attn.k_proj.bias", 2), out_bf16=kv2)
         self.attn_fwd(plan, q2, kv2, kv2[:, d:], d, 2 * d, 2 * d, ctx, lse, pad_e, B, H, Sd, Se, False)
+        z = self.buf(a, f"zbuf{Md}", (Md, d), BF16)
         self.gemm(plan, ctx, st.p16(lp + ".encoder_attn.out_proj.weight"), Md, d, d, d, d,
-                  bias=st.p32(lp + ".encoder_attn.out_proj.bias"), residual=x_f32, out_f32=pre,
-                  dropout_p=p_drop, dropout_tag=drop_tag)
-        self.ln_fwd(plan, pre, lp + ".encoder_attn_layer_norm", y_f32, y_b16, mean, rstd, Md)
+                  bias=st.p32(lp + ".encoder_attn.out_proj.bias"), out_bf16=z)
+        self.ln_fwd(plan, z, x_f32, lp + ".encoder_attn_layer_norm", pre, y_f32, y_b16, mean, rstd, Md, drop=(p_drop, drop_tag))
         return y_f32, y_b16
 
     # ------------------------------------------------------------------ forward plans
@@ -420,31 +423,33 @@ class Engine:
                  0, _ptr(acc2), float(factor), _ptr(lm_loss), _ptr(a["loss"]), int(add_total), plan.stream)
 
     # ------------------------------------------------------------------ backward plans
-    def _ffn_block_bwd(self, plan, a, tag, lp, dy, M, F, x_in_b16, p_drop, drop_tag, acc, dres_out):
-        """dy: grad wrt block output (fp32).  Writes grad wrt block input into dres_out (fp32)."""
+    # Backward convention: the gradient w.r.t. a block's output arrives as an fp32 part dyA (the
+    # residual path: dpre of the following LayerNorm) plus a bf16 part dyB (dgrad GEMM output of the
+    # consuming Linear); either may be None.  A block writes the fp32 part of its input gradient
+    # into dpre_out (fresh buffer, distinct from dyA) and the bf16 part into dyb_out.
+    def _ffn_block_bwd(self, plan, a, tag, lp, dyA, dyB, M, F, x_in_b16, p_drop, drop_tag, acc, dpre_out, dyb_out):
         st, d = self.store, self.cfg.d_model
-        dpre = self.buf(a, "g.dpre", (M, d), F32) if M == a["Me"] else self.buf(a, "g.dpre_d", (M, d), F32)
-        dz = self.buf(a, "g.dz", (M, d), BF16) if M == a["Me"] else self.buf(a, "g.dz_d", (M, d), BF16)
-        du = self.buf(a, "g.du", (M, F), BF16) if M == a["Me"] else self.buf(a, "g.du_d", (M, F), BF16)
-        self.ln_bwd(plan, dy, a[tag + "pre3"], a[tag + "mean3"], a[tag + "rstd3"], lp + ".final_layer_norm", dpre, dz,
+        sfx = "" if M == a["Me"] else "_d"
+        dz = self.buf(a, "g.dz" + sfx, (M, d), BF16)
+        du = self.buf(a, "g.du" + sfx, (M, F), BF16)
+        self.ln_bwd(plan, dyA, dyB, a[tag + "pre3"], a[tag + "mean3"], a[tag + "rstd3"], lp + ".final_layer_norm", dpre_out, dz,
                     st.g(lp + ".fc2.bias"), M, drop_out=(p_drop, drop_tag))
-        # dW2[d, F] = dz^T h ; du = (dz W2) * gelu'(u) ; db1 = colsum(du) ; dW1[F, d] = du^T x ; dx = du W1 + dpre
+        # dW2[d, F] = dz^T h ; du = (dz W2) * gelu'(u) ; db1 = colsum(du) ; dW1[F, d] = du^T x ; dx = du W1
         self.gemm(plan, dz, a[tag + "h"], d, F, M, d, F, a_mn=1, b_mn=1, out_f32=st.g(lp + ".fc2.weight"), ld_f32=F, accumulate=acc)
         self.gemm(plan, dz, st.p16(lp + ".fc2.weight"), M, F, d, d, F, b_mn=1, act=L.ACT_GELU_GRAD, aux=a[tag + "u"], ld_aux=F, out_bf16=du)
         self.colsum(plan, du, F, st.g(lp + ".fc1.bias"), M, F)
         self.gemm(plan, du, x_in_b16, F, d, M, F, d, a_mn=1, b_mn=1, out_f32=st.g(lp + ".fc1.weight"), ld_f32=d, accumulate=acc)
-        self.gemm(plan, du, st.p16(lp + ".fc1.weight"), M, d, F, F, d, b_mn=1, residual=dpre, out_f32=dres_out)
+        self.gemm(plan, du, st.p16(lp + ".fc1.weight"), M, d, F, F, d, b_mn=1, out_bf16=dyb_out)
 
-    def _self_block_bwd(self, plan, a, tag, lp, dy, M, B, S, H, pad, causal, x_in_b16, p_drop, drop_tag, acc, dres_out):
+    def _self_block_bwd(self, plan, a, tag, lp, dyA, dyB, M, B, S, H, pad, causal, x_in_b16, p_drop, drop_tag, acc, dpre_out, dyb_out):
         st, d = self.store, self.cfg.d_model
         sfx = "" if M == a["Me"] else "_d"
-        dpre = self.buf(a, "g.dpre" + sfx, (M, d), F32)
         dz = self.buf(a, "g.dz" + sfx, (M, d), BF16)
         dctx = self.buf(a, "g.dctx" + sfx, (M, d), BF16)
         dqkv = self.buf(a, "g.dqkv" + sfx, (M, 3 * d), BF16)
         dscr = self.buf(a, "g.dscr" + sfx, (B * H * S,), F32)
         qkv = a[tag + "qkv"]
-        self.ln_bwd(plan, dy, a[tag + "pre1"], a[tag + "mean1"], a[tag + "rstd1"], lp + ".self_attn_layer_norm", dpre, dz,
+        self.ln_bwd(plan, dyA, dyB, a[tag + "pre1"], a[tag + "mean1"], a[tag + "rstd1"], lp + ".self_attn_layer_norm", dpre_out, dz,
                     st.g(lp + ".self_attn.out_proj.bias"), M, drop_out=(p_drop, drop_tag))
         self.gemm(plan, dz, a[tag + "ctx"], d, d, M, d, d, a_mn=1, b_mn=1, out_f32=st.g(lp + ".self_attn.out_proj.weight"), ld_f32=d, accumulate=acc)
         self.gemm(plan, dz, st.p16(lp + ".self_attn.out_proj.weight"), M, d, d, d, d, b_mn=1, out_bf16=dctx)
@@ -452,19 +457,18 @@ class Engine:
                       dqkv, dqkv[:, d:], dqkv[:, 2 * d:], 3 * d, 3 * d, 3 * d, B, H, S, S, causal)
         self.colsum(plan, dqkv, 3 * d, st.g(lp + ".self_attn.q_proj.bias", 3), M, 3 * d)
         self.gemm(plan, dqkv, x_in_b16, 3 * d, d, M, 3 * d, d, a_mn=1, b_mn=1, out_f32=st.g(lp + ".self_attn.q_proj.weight", 3), ld_f32=d, accumulate=acc)
-        self.gemm(plan, dqkv, st.p16(lp + ".self_attn.q_proj.weight", 3 * d), M, d, 3 * d, 3 * d, d, b_mn=1, residual=dpre, out_f32=dres_out)
+        self.gemm(plan, dqkv, st.p16(lp + ".self_attn.q_proj.weight", 3 * d), M, d, 3 * d, 3 * d, d, b_mn=1, out_bf16=dyb_out)
 
-    def _cross_block_bwd(self, plan, a, tag, lp, dy, Md, Me, B, Sd, Se, H, pad_e, x_in_b16, enc_b16, p_drop, drop_tag, acc,
-                         dres_out, denc, first_cross):
+    def _cross_block_bwd(self, plan, a, tag, lp, dyA, dyB, Md, Me, B, Sd, Se, H, pad_e, x_in_b16, enc_b16, p_drop, drop_tag, acc,
+                         dpre_out, dyb_out, denc, first_cross):
         st, d = self.store, self.cfg.d_model
-        dpre = self.buf(a, "g.dpre_d", (Md, d), F32)
         dz = self.buf(a, "g.dz_d", (Md, d), BF16)
         dctx = self.buf(a, "g.dctx_d", (Md, d), BF16)
         dq2 = self.buf(a, "g.dq2", (Md, d), BF16)
         dkv2 = self.buf(a, "g.dkv2", (Me, 2 * d), BF16)
         dscr = self.buf(a, "g.dscr_d", (B * H * Sd,), F32)
         q2, kv2 = a[tag + "q2"], a[tag + "kv2"]
-        self.ln_bwd(plan, dy, a[tag + "pre2"], a[tag + "mean2"], a[tag + "rstd2"], lp + ".encoder_attn_layer_norm", dpre, dz,
+        self.ln_bwd(plan, dyA, dyB, a[tag + "pre2"], a[tag + "mean2"], a[tag + "rstd2"], lp + ".encoder_attn_layer_norm", dpre_out, dz,
                     st.g(lp + ".encoder_attn.out_proj.bias"), Md, drop_out=(p_drop, drop_tag))
         self.gemm(plan, dz, a[tag + "ctx2"], d, d, Md, d, d, a_mn=1, b_mn=1, out_f32=st.g(lp + ".encoder_attn.out_proj.weight"), ld_f32=d, accumulate=acc)
         self.gemm(plan, dz, st.p16(lp + ".encoder_attn.out_proj.weight"), Md, d, d, d, d, b_mn=1, out_bf16=dctx)
@@ -476,7 +480,7 @@ class Engine:
         self.gemm(plan, dkv2, enc_b16, 2 * d, d, Me, 2 * d, d, a_mn=1, b_mn=1, out_f32=st.g(lp + ".encoder_attn.k_proj.weight", 2), ld_f32=d, accumulate=acc)
         self.gemm(plan, dkv2, st.p16(lp + ".encoder_attn.k_proj.weight", 2 * d), Me, d, 2 * d, 2 * d, d, b_mn=1, out_f32=denc,
                   accumulate=0 if first_cross else 1)
-        self.gemm(plan, dq2, st.p16(lp + ".encoder_attn.q_proj.weight"), Md, d, d, d, d, b_mn=1, residual=dpre, out_f32=dres_out)
+        self.gemm(plan, dq2, st.p16(lp + ".encoder_attn.q_proj.weight"), Md, d, d, d, d, b_mn=1, out_bf16=dyb_out)
 
     def _build_train_fwd(self, a):
         cfg = self.cfg
@@ -509,51 +513,54 @@ class Engine:
             bwd.add(_zero, st.G[:st.small_end])
         gscale = self.buf(a, "ce_gscale", (1,), F32)
         dlog = self.buf(a, "dlogits", (Md, V), BF16)
-        dyA = self.buf(a, "g.dyA_d", (Md, d), F32)
-        dyB = self.buf(a, "g.dyB_d", (Md, d), F32)
+        dpre_d = [self.buf(a, "g.dpreA_d", (Md, d), F32), self.buf(a, "g.dpreB_d", (Md, d), F32)]
+        dyb_d = self.buf(a, "g.dyb_d", (Md, d), BF16)
         E16 = st.p16(self.n("shared.weight"))
         bwd.add(self.lib.kmb_ce_gscale, _ptr(a["ce_acc"]), _ptr(self.upstream), float(a["lm_factor"]), _ptr(gscale), bwd.stream)
         self.gemm(bwd, a["dec_b16"], E16, Md, V, d, d, d, tile_n=256, mode=L.EPI_CE_GRAD, bias=a["flb"], labels=a["labels"],
                   ce_lse=a["ce_lse"], ce_gscale=gscale, out_bf16=dlog, ld_bf16=V)
-        self.gemm(bwd, dlog, E16, Md, d, V, V, d, b_mn=1, out_f32=dyA)
+        self.gemm(bwd, dlog, E16, Md, d, V, V, d, b_mn=1, out_bf16=dyb_d)
         self.gemm(bwd, dlog, a["dec_b16"], V, d, Md, V, d, a_mn=1, b_mn=1, out_f32=st.g(self.n("shared.weight")), ld_f32=d, accumulate=acc)
         # decoder layers, last to first
-        dy, other = dyA, dyB
+        dyA, dyB, flip = None, dyb_d, 0
         denc = self.buf(a, "g.denc", (Me, d), F32)
         Hd, Fd = cfg.decoder_attention_heads, cfg.decoder_ffn_dim
         pad_e = a["pad_e"] if a["has_mask_e"] else None
         first_cross = True
         for l in reversed(range(cfg.decoder_layers)):
             lp, tag = self.n(f"decoder.layers.{l}"), f"d{l}."
-            self._ffn_block_bwd(bwd, a, tag, lp, dy, Md, Fd, a[tag + "mid2_b16"], p_drop, 102 + 3 * l, acc, other)
-            dy, other = other, dy
-            self._cross_block_bwd(bwd, a, tag, lp, dy, Md, Me, B, Sd, Se, Hd, pad_e, a[tag + "mid_b16"], a["enc_b16"], p_drop,
-                                  101 + 3 * l, acc, other, denc, first_cross)
+            self._ffn_block_bwd(bwd, a, tag, lp, dyA, dyB, Md, Fd, a[tag + "mid2_b16"], p_drop, 102 + 3 * l, acc, dpre_d[flip], dyb_d)
+            dyA, dyB, flip = dpre_d[flip], dyb_d, flip ^ 1
+            self._cross_block_bwd(bwd, a, tag, lp, dyA, dyB, Md, Me, B, Sd, Se, Hd, pad_e, a[tag + "mid_b16"], a["enc_b16"], p_drop,
+                                  101 + 3 * l, acc, dpre_d[flip], dyb_d, denc, first_cross)
             first_cross = False
-            dy, other = other, dy
-            self._self_block_bwd(bwd, a, tag, lp, dy, Md, B, Sd, Hd, a["pad_d"], True, a[tag + "in_b16"], p_drop, 100 + 3 * l, acc, other)
-            dy, other = other, dy
+            dyA, dyB, flip = dpre_d[flip], dyb_d, flip ^ 1
+            self._self_block_bwd(bwd, a, tag, lp, dyA, dyB, Md, B, Sd, Hd, a["pad_d"], True, a[tag + "in_b16"], p_drop, 100 + 3 * l, acc,
+                                 dpre_d[flip], dyb_d)
+            dyA, dyB, flip = dpre_d[flip], dyb_d, flip ^ 1
         # decoder embedding
-        demb_d = self.buf(a, "g.dpre_d", (Md, d), F32)
+        demb_d = dpre_d[flip]
         scale = math.sqrt(d) if cfg.scale_embedding else 1.0
-        self.ln_bwd(bwd, dy, a["d.emb_pre"], a["d.emb_mean"], a["d.emb_rstd"], self.n("decoder.layernorm_embedding"), demb_d, None, None, Md,
+        self.ln_bwd(bwd, dyA, dyB, a["d.emb_pre"], a["d.emb_mean"], a["d.emb_rstd"], self.n("decoder.layernorm_embedding"), demb_d, None, None, Md,
                     drop_in=(p_drop, 2))
         bwd.add(self.lib.kmb_embed_bwd, _ptr(demb_d), _ptr(a["ids_d"]), 0, _ptr(st.g(self.n("shared.weight"))), 0,
                 _ptr(st.g(self.n("decoder.embed_positions.weight"))), B, Sd, d, cfg.extra_pos_embeddings, cfg.pad_token_id,
                 scale, acc, bwd.stream)
         # encoder layers
-        dyE = self.buf(a, "g.dyE", (Me, d), F32)
-        dy, other = denc, dyE
+        dpre_e = [self.buf(a, "g.dpreA_e", (Me, d), F32), self.buf(a, "g.dpreB_e", (Me, d), F32)]
+        dyb_e = self.buf(a, "g.dyb_e", (Me, d), BF16)
+        dyA, dyB, flip = denc, None, 0
         He, Fe = cfg.encoder_attention_heads, cfg.encoder_ffn_dim
         for l in reversed(range(cfg.encoder_layers)):
             lp, tag = self.n(f"encoder.layers.{l}"), f"e{l}."
-            self._ffn_block_bwd(bwd, a, tag, lp, dy, Me, Fe, a[tag + "x1_b16"], p_drop, 11 + 2 * l, acc, other)
-            dy, other = other, dy
-            self._self_block_bwd(bwd, a, tag, lp, dy, Me, B, Se, He, pad_e, False, a[tag + "in_b16"], p_drop, 10 + 2 * l, acc, other)
-            dy, other = other, dy
-        demb_e = self.buf(a, "g.dpre", (Me, d), F32)
+            self._ffn_block_bwd(bwd, a, tag, lp, dyA, dyB, Me, Fe, a[tag + "x1_b16"], p_drop, 11 + 2 * l, acc, dpre_e[flip], dyb_e)
+            dyA, dyB, flip = dpre_e[flip], dyb_e, flip ^ 1
+            self._self_block_bwd(bwd, a, tag, lp, dyA, dyB, Me, B, Se, He, pad_e, False, a[tag + "in_b16"], p_drop, 10 + 2 * l, acc,
+                                 dpre_e[flip], dyb_e)
+            dyA, dyB, flip = dpre_e[flip], dyb_e, flip ^ 1
+        demb_e = dpre_e[flip]
         dvis = self.buf(a, "g.dvis", (max(R, 1), d), BF16)
-        self.ln_bwd(bwd, dy, a["e.emb_pre"], a["e.emb_mean"], a["e.emb_rstd"], self.n("encoder.layernorm_embedding"), demb_e, None, None, Me,
+        self.ln_bwd(bwd, dyA, dyB, a["e.emb_pre"], a["e.emb_mean"], a["e.emb_rstd"], self.n("encoder.layernorm_embedding"), demb_e, None, None, Me,
                     drop_in=(p_drop, 1))
         bwd.add(self.lib.kmb_embed_bwd, _ptr(demb_e), _ptr(a["ids_e"]), _ptr(a["slot"]), _ptr(st.g(self.n("shared.weight"))),
                 _ptr(dvis), _ptr(st.g(self.n("encoder.embed_positions.weight"))), B, Se, d, cfg.extra_pos_embeddings,
@@ -801,12 +808,12 @@ class Engine:
             ctx = torch.empty(n, d, dtype=BF16, device=dev)
             self._attn_strided(plan, qkv[:, :d].view(n, 1, H, 64).permute(0, 2, 1, 3), K, V,
                                ctx.view(n, 1, H, 64).permute(0, 2, 1, 3), None, n, H, 1, T)
-            pre = torch.empty(n, d, dtype=F32, device=dev)
+            pre = torch.empty(n, d, dtype=BF16, device=dev)
             y_f32 = torch.empty(n, d, dtype=F32, device=dev)
             y_b16 = torch.empty(n, d, dtype=BF16, device=dev)
             self.gemm(plan, ctx, st.p16(lp + ".self_attn.out_proj.weight"), n, d, d, d, d,
-                      bias=st.p32(lp + ".self_attn.out_proj.bias"), residual=x_f32, out_f32=pre)
-            self.ln_fwd(plan, pre, lp + ".self_attn_layer_norm", y_f32, y_b16, None, None, n)
+                      bias=st.p32(lp + ".self_attn.out_proj.bias"), out_bf16=pre)
+            self.ln_fwd(plan, pre, x_f32, lp + ".self_attn_layer_norm", None, y_f32, y_b16, None, None, n)
             # --- cross attention with static cache
             cc = lc.get("encoder_decoder")
             q2 = torch.empty(n, d, dtype=BF16, device=dev)
@@ -827,20 +834,20 @@ class Engine:
             ctx2 = torch.empty(n, d, dtype=BF16, device=dev)
             self._attn_strided(plan, q2.view(n, 1, H, 64).permute(0, 2, 1, 3), K2, V2,
                                ctx2.view(n, 1, H, 64).permute(0, 2, 1, 3), enc_pad_u8, n, H, 1, Se)
-            pre2 = torch.empty(n, d, dtype=F32, device=dev)
+            pre2 = torch.empty(n, d, dtype=BF16, device=dev)
             z_f32 = torch.empty(n, d, dtype=F32, device=dev)
             z_b16 = torch.empty(n, d, dtype=BF16, device=dev)
             self.gemm(plan, ctx2, st.p16(lp + ".encoder_attn.out_proj.weight"), n, d, d, d, d,
-                      bias=st.p32(lp + ".encoder_attn.out_proj.bias"), residual=y_f32, out_f32=pre2)
-            self.ln_fwd(plan, pre2, lp + ".encoder_attn_layer_norm", z_f32, z_b16, None, None, n)
+                      bias=st.p32(lp + ".encoder_attn.out_proj.bias"), out_bf16=pre2)
+            self.ln_fwd(plan, pre2, y_f32, lp + ".encoder_attn_layer_norm", None, z_f32, z_b16, None, None, n)
             # --- FFN
             hbuf = torch.empty(n, F, dtype=BF16, device=dev)
-            pre3 = torch.empty(n, d, dtype=F32, device=dev)
+            pre3 = torch.empty(n, d, dtype=BF16, device=dev)
             x_f32 = torch.empty(n, d, dtype=F32, device=dev)
             x_b16 = torch.empty(n, d, dtype=BF16, device=dev)
             self.gemm(plan, z_b16, st.p16(lp + ".fc1.weight"), n, F, d, d, d, bias=st.p32(lp + ".fc1.bias"), act=L.ACT_GELU, out_bf16=hbuf)
-            self.gemm(plan, hbuf, st.p16(lp + ".fc2.weight"), n, d, F, F, F, bias=st.p32(lp + ".fc2.bias"), residual=z_f32, out_f32=pre3)
-            self.ln_fwd(plan, pre3, lp + ".final_layer_norm", x_f32, x_b16, None, None, n)
+            self.gemm(plan, hbuf, st.p16(lp + ".fc2.weight"), n, d, F, F, F, bias=st.p32(lp + ".fc2.bias"), out_bf16=pre3)
+            self.ln_fwd(plan, pre3, z_f32, lp + ".final_layer_norm", None, x_f32, x_b16, None, None, n)
             plan.run(); plan.calls.clear()
             keep += [qkv, ctx, pre, y_f32, y_b16, q2, ctx2, pre2, z_f32, z_b16, hbuf, pre3, K, V, K2, V2]
             new_caches.append({"self": {"prev_key": K, "prev_value": V, "prev_key_padding_mask": None},

@@ -51,8 +51,8 @@ _PROTOS = {
     "kmb_embed_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                       c_float, c_int, c_void_p],
     "kmb_box_wgrad": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
-    "kmb_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
-    "kmb_layernorm_bwd": [c_void_p] * 10 + [c_int, c_int, c_float, c_uint32, c_float, c_uint32, c_void_p, c_void_p],
+    "kmb_layernorm_fwd": [c_void_p] * 9 + [c_int, c_int, c_float, c_uint32, c_void_p, c_void_p],
+    "kmb_layernorm_bwd": [c_void_p] * 11 + [c_int, c_int, c_float, c_uint32, c_float, c_uint32, c_void_p, c_void_p],
     "kmb_colsum_bf16": [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p],
     "kmb_gather_rows_bf16": [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p],
     "kmb_scatter_add_rows": [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p],
