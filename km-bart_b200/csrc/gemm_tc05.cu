@@ -15,6 +15,7 @@
 // (SURVEY.md §2.3(b) K2,K5,K7,K8,K10) — see include/kmbart.h for the call-site map.
 #include <cuda.h>
 #include <stdio.h>
+#include <string.h>
 #include <mutex>
 #include "common.cuh"
 #include "../../include/kmbart.h"
@@ -30,6 +31,8 @@ struct GemmParams {
   int m_tiles, n_tiles, k_blocks;
   KmbGemmEpilogue e;
   int vec_ok;  // all leading dims / pointers allow 16-byte row-segment access
+  int tma_out; // bf16 outputs leave through smem + TMA bulk stores (tmOut / tmPre valid)
+  int split_k, kb_per_split;  // split-K work items; partial sums are reduced with fp32 red.global.add
   uint32_t drop_thresh16;
   float drop_scale;
 };
@@ -218,7 +221,29 @@ __device__ __forceinline__ void epilogue_linear(const GemmParams& p, float4* st,
         if (j < ncols) v[j] += rp[(int64_t)lane * e.ld_res + j];
     }
   }
-  if (e.out_f32) {
+  if (e.out_f32 && p.split_k > 1) {
+    // split-K partial: reduce into the (pre-zeroed or accumulating) fp32 output with vector reds
+    float* op = e.out_f32 + (int64_t)row0 * e.ld_f32 + col0;
+    if (full) {
+      tile_put_row(st, lane, v);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3), grp = lane & 7;
+        if (rr < rows_valid) {
+          const float4 x = st[rr * 8 + (grp ^ (rr & 7))];
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op + (int64_t)rr * e.ld_f32 + 4 * grp), "f"(x.x),
+                       "f"(x.y), "f"(x.z), "f"(x.w)
+                       : "memory");
+        }
+      }
+      __syncwarp();
+    } else if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) atomicAdd(op + (int64_t)lane * e.ld_f32 + j, v[j]);
+    }
+  } else if (e.out_f32) {
     float* op = e.out_f32 + (int64_t)row0 * e.ld_f32 + col0;
     if (full) {
       if (e.accumulate) {
@@ -250,9 +275,33 @@ __device__ __forceinline__ void epilogue_linear(const GemmParams& p, float4* st,
   }
 }
 
+// ------------------------------------------------------------------ epilogue fast path: bf16 via TMA store
+// 32 rows x 64 columns (two tcgen05.ld chunks) are packed to bf16 and written into the warp's 4 KB
+// staging tile in the SWIZZLE_128B pattern (16-byte piece p of row r at r*128 + ((p ^ (r & 7)) << 4)),
+// which is both bank-conflict free for thread-per-row stores and the layout a 128B-swizzled tensor
+// map expects; one elected lane then issues an asynchronous bulk store.  Rows / columns outside
+// [M, N] are clipped by the TMA unit.
+__device__ __forceinline__ void stage_bf16_pair_and_store(float4* st, int lane, const float (&v)[64], const void* tmap,
+                                                          int col0, int row0) {
+  if (lane == 0) tma_store_wait_read();  // previous bulk store has drained the tile
+  __syncwarp();
+  uint4* sp = reinterpret_cast<uint4*>(st);
+#pragma unroll
+  for (int pc = 0; pc < 8; ++pc)
+    sp[lane * 8 + (pc ^ (lane & 7))] = make_uint4(pack_bf16(v[8 * pc], v[8 * pc + 1]), pack_bf16(v[8 * pc + 2], v[8 * pc + 3]),
+                                                  pack_bf16(v[8 * pc + 4], v[8 * pc + 5]), pack_bf16(v[8 * pc + 6], v[8 * pc + 7]));
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tmap, st, col0, row0);
+    tma_store_commit();
+  }
+}
+
 template <int BN, int ELT, int A_MN, int B_MN>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmPre,
                  const GemmParams p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
@@ -297,7 +346,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -306,8 +355,10 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int m0 = (t % p.m_tiles) * BM;
-        const int n0 = (t / p.m_tiles) * BN;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        const int n0 = ((t / p.m_tiles) % p.n_tiles) * BN;
+        const int kb0 = (t / (p.m_tiles * p.n_tiles)) * p.kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + A_TILE_BYTES;
@@ -343,7 +394,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        const int kb_lo = (t / (p.m_tiles * p.n_tiles)) * p.kb_per_split;
+        const int kb_n = min(p.k_blocks, kb_lo + p.kb_per_split) - kb_lo;
+        for (int kb = 0; kb < kb_n; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
@@ -377,7 +430,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t drop_key = 0;
     if (p.drop_thresh16 && p.e.dropout_seed) drop_key = dropout_key(*p.e.dropout_seed, p.e.dropout_tag);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
+      const int m_blk = t % p.m_tiles, n_blk = (t / p.m_tiles) % p.n_tiles;
       const int row0 = m_blk * BM + q * 32;
       const int row = row0 + lane;
       const int n0 = n_blk * BN;
@@ -388,7 +441,73 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int rows_valid = p.M - row0;
       rows_valid = rows_valid > 32 ? 32 : rows_valid;
 
-      if (p.e.mode == KMB_EPI_LINEAR) {
+      if (p.e.mode == KMB_EPI_LINEAR && p.tma_out && BN >= 64) {
+        // ---- fast path: bias / activation -> bf16 -> TMA store, 64 columns at a time
+        const KmbGemmEpilogue& e = p.e;
+#pragma unroll 1
+        for (int pr = half; pr < BN / 64; pr += 2) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(taddr + pr * 64, r0);
+          tmem_ld32(taddr + pr * 64 + 32, r1);
+          tmem_ld_wait();
+          const int col0 = n0 + pr * 64;
+          if (rows_valid > 0 && col0 < p.N) {
+            float v[64];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
+            if (e.alpha != 1.0f) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) v[j] *= e.alpha;
+            }
+            if (e.bias) {
+              if (col0 + 64 <= p.N) {
+                const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float4 t4 = __ldg(b4 + j);
+                  v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 64; ++j)
+                  if (col0 + j < p.N) v[j] += __ldg(e.bias + col0 + j);
+              }
+            }
+            if (e.act == KMB_ACT_GELU) {
+              if (e.out_preact) stage_bf16_pair_and_store(st, lane, v, &tmPre, col0, row0);
+#pragma unroll
+              for (int j = 0; j < 64; ++j) v[j] = gelu_erf(v[j]);
+            } else if (e.act == KMB_ACT_TANH) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) v[j] = tanhf(v[j]);
+            } else if (e.act == KMB_ACT_GELU_GRAD || e.act == KMB_ACT_TANH_GRAD) {
+              if (lane == 0) tma_store_wait_read();  // the staging tile doubles as the aux transpose buffer
+              __syncwarp();
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                float a[32];
+                const int cc = col0 + hh * 32;
+                const bf16* ap = reinterpret_cast<const bf16*>(e.aux) + (int64_t)row0 * e.ld_aux + cc;
+                if (cc + 32 <= p.N && p.vec_ok) {
+                  tile_load_bf16(st, lane, ap, e.ld_aux, rows_valid, a);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    a[j] = (row_ok && cc + j < p.N) ? __bfloat162float(ap[(int64_t)lane * e.ld_aux + j]) : 0.f;
+                }
+                if (e.act == KMB_ACT_GELU_GRAD) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[hh * 32 + j] *= gelu_erf_grad(a[j]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[hh * 32 + j] *= (1.f - a[j] * a[j]);
+                }
+              }
+            }
+            stage_bf16_pair_and_store(st, lane, v, &tmOut, col0, row0);
+          }
+        }
+      } else if (p.e.mode == KMB_EPI_LINEAR) {
 #pragma unroll 1
         for (int c = half; c < BN / 32; c += 2) {
           uint32_t r[32];
@@ -448,36 +567,28 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           p.e.ce_max[(int64_t)row * (2 * p.n_tiles) + 2 * n_blk + half] = mx;
           p.e.ce_sum[(int64_t)row * (2 * p.n_tiles) + 2 * n_blk + half] = sm;
         }
-      } else {  // KMB_EPI_CE_GRAD
+      } else {  // KMB_EPI_CE_GRAD: dlogits = (softmax - onehot) * gscale, bf16, through the TMA store path
         const int64_t label = row_ok ? p.e.labels[row] : -100;
         const float lse = row_ok ? p.e.ce_lse[row] : 0.f;
         const float gs = (label >= 0) ? *p.e.ce_gscale : 0.f;
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c * 32, r);
+        for (int pr = half; pr < BN / 64; pr += 2) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(taddr + pr * 64, r0);
+          tmem_ld32(taddr + pr * 64 + 32, r1);
           tmem_ld_wait();
-          const int col0 = n0 + c * 32;
-          int ncols = p.N - col0;
-          ncols = ncols > 32 ? 32 : ncols;
-          if (rows_valid > 0 && ncols > 0) {
-            float v[32];
+          const int col0 = n0 + pr * 64;
+          if (rows_valid > 0 && col0 < p.N) {
+            float v[64];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(r[j]) * p.e.alpha;
-              if (p.e.bias && j < ncols) x += __ldg(p.e.bias + col0 + j);
-              float pr = __expf(x - lse);
-              if (col0 + j == (int)label) pr -= 1.f;
-              v[j] = pr * gs;
+            for (int j = 0; j < 64; ++j) {
+              float x = __uint_as_float(j < 32 ? r0[j & 31] : r1[j & 31]) * p.e.alpha;
+              if (p.e.bias && col0 + j < p.N) x += __ldg(p.e.bias + col0 + j);
+              float pv = __expf(x - lse);
+              if (col0 + j == (int)label) pv -= 1.f;
+              v[j] = pv * gs;
             }
-            bf16* og = reinterpret_cast<bf16*>(p.e.out_bf16) + (int64_t)row0 * p.e.ld_bf16 + col0;
-            if (ncols == 32 && p.vec_ok) {
-              tile_store_bf16(st, lane, og, p.e.ld_bf16, rows_valid, v);
-            } else if (row_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) og[(int64_t)lane * p.e.ld_bf16 + j] = __float2bfloat16(v[j]);
-            }
+            stage_bf16_pair_and_store(st, lane, v, &tmOut, col0, row0);
           }
         }
       }
@@ -485,6 +596,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_read();  // staging smem must outlive the last bulk store's read
   }
 
   tc_fence_before();
@@ -553,7 +665,8 @@ static int num_sms() {
 }
 
 template <int BN, int ELT, int A_MN, int B_MN>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmPre,
+                  const GemmParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
   auto kern = gemm_tc05_kernel<BN, ELT, A_MN, B_MN>;
   static bool attr_set = false;  // per instantiation
@@ -565,23 +678,23 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
     }
     attr_set = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles;
+  const int tiles = p.m_tiles * p.n_tiles * p.split_k;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 384, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+  kern<<<grid, 384, C::SMEM_BYTES, st>>>(tmA, tmB, tmOut, tmPre, p);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }
 
 template <int BN, int ELT>
-static int launch_major(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                        const GemmParams& p, cudaStream_t st) {
+static int launch_major(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                        const CUtensorMap& tmPre, const GemmParams& p, cudaStream_t st) {
   // an MN-major B tile is built from 128-byte-wide chunks, so BN must cover one chunk
   constexpr bool kBmnOk = BN >= (ELT == 0 ? 64 : 32);
-  if (!a_mn && !b_mn) return launch<BN, ELT, 0, 0>(tmA, tmB, p, st);
-  if (a_mn && !b_mn) return launch<BN, ELT, 1, 0>(tmA, tmB, p, st);
+  if (!a_mn && !b_mn) return launch<BN, ELT, 0, 0>(tmA, tmB, tmOut, tmPre, p, st);
+  if (a_mn && !b_mn) return launch<BN, ELT, 1, 0>(tmA, tmB, tmOut, tmPre, p, st);
   if constexpr (kBmnOk) {
-    if (!a_mn && b_mn) return launch<BN, ELT, 0, 1>(tmA, tmB, p, st);
-    return launch<BN, ELT, 1, 1>(tmA, tmB, p, st);
+    if (!a_mn && b_mn) return launch<BN, ELT, 0, 1>(tmA, tmB, tmOut, tmPre, p, st);
+    return launch<BN, ELT, 1, 1>(tmA, tmB, tmOut, tmPre, p, st);
   }
   kmb_set_last_error("kmb_gemm: tile_n too narrow for an MN-major B operand", __FILE__, __LINE__);
   return KMB_ERR_ARG;
@@ -590,10 +703,12 @@ static int launch_major(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtens
 }  // namespace kmb
 
 extern "C" int kmb_gemm_pick_tile_n(int M, int N) {
-  // Largest tile whose tile count still fills the 148 SMs reasonably; small-M (decode)
-  // problems get narrow tiles so that many CTAs stream the weights concurrently.
+  // Wide tiles halve the operand traffic per flop (measured: 128-wide tiles saturate near 0.75 PFLOP/s
+  // on L2 bandwidth, 256-wide reach ~1.3); narrow tiles only win when they are needed to fill the SMs
+  // (small-M decode problems streaming the weights).
   const int mt = (M + kmb::BM - 1) / kmb::BM;
   const int cands[4] = {256, 128, 64, 32};
+  const double mainloop[4] = {1.0, 0.6, 0.4, 0.25};
   int best = 32;
   double best_score = -1.0;
   for (int i = 0; i < 4; ++i) {
@@ -603,8 +718,7 @@ extern "C" int kmb_gemm_pick_tile_n(int M, int N) {
     const int waves = (tiles + 147) / 148;
     const double eff = (double)tiles / (waves * 148.0);           // SM fill
     const double npad = (double)N / (((N + bn - 1) / bn) * bn);   // useful columns
-    const double shape = bn >= 128 ? 1.0 : (bn == 64 ? 0.8 : 0.6);  // MMA efficiency of narrow tiles
-    const double score = eff * npad * shape;
+    const double score = eff * npad * mainloop[i];
     if (score > best_score + 1e-9) { best_score = score; best = bn; }
   }
   return best;
@@ -680,11 +794,54 @@ extern "C" int kmb_gemm(const void* A, const void* B, int M, int N, int K, int64
   else rc = make_tmap(&tmB, B, elt, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, bk, bk);
   if (rc) return rc;
 
+  // split-K: weight-gradient shaped problems (few output tiles, long K) that accumulate into fp32
+  p.split_k = 1;
+  p.kb_per_split = p.k_blocks;
+  if (epi->mode == KMB_EPI_LINEAR && epi->accumulate && epi->out_f32 && !epi->out_bf16 && !epi->residual && !epi->bias &&
+      epi->act == KMB_ACT_NONE && epi->dropout_p <= 0.f) {
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int sms = num_sms();
+    int best = 1;
+    double best_eff = 0.0;
+    for (int sk = 1; sk <= 16; ++sk) {
+      if (p.k_blocks / sk < 8 && sk > 1) break;
+      const int items = tiles * sk;
+      const double eff = (double)items / (((items + sms - 1) / sms) * (double)sms);
+      if (eff > best_eff + 0.02) { best_eff = eff; best = sk; }
+    }
+    if (best > 1) {
+      p.kb_per_split = (p.k_blocks + best - 1) / best;
+      p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+    }
+  }
+
+  // bf16 outputs of plain Linear / CE-grad epilogues leave through TMA bulk stores
+  CUtensorMap tmOut, tmPre;
+  memset(&tmOut, 0, sizeof tmOut);
+  memset(&tmPre, 0, sizeof tmPre);
+  p.tma_out = 0;
+  const bool lin_fast = epi->mode == KMB_EPI_LINEAR && epi->out_bf16 && !epi->out_f32 && !epi->residual &&
+                        epi->dropout_p <= 0.f;
+  if ((lin_fast || epi->mode == KMB_EPI_CE_GRAD) && tile_n >= 64 && (epi->ld_bf16 % 8) == 0 && al16(epi->out_bf16) &&
+      (!epi->out_preact || al16(epi->out_preact))) {
+    rc = make_tmap(&tmOut, epi->out_bf16, 0, (uint64_t)M, (uint64_t)N, (uint64_t)epi->ld_bf16, 64, 32);
+    if (rc) return rc;
+    if (epi->out_preact) {
+      rc = make_tmap(&tmPre, epi->out_preact, 0, (uint64_t)M, (uint64_t)N, (uint64_t)epi->ld_bf16, 64, 32);
+      if (rc) return rc;
+    }
+    p.tma_out = 1;
+  }
+  if (epi->mode == KMB_EPI_CE_GRAD && !p.tma_out) {
+    kmb_set_last_error("kmb_gemm: CE_GRAD needs tile_n >= 64 and a 16-byte aligned bf16 output", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define KMB_DISPATCH_BN(BNV)                                                        \
   case BNV:                                                                         \
-    return elt == 0 ? launch_major<BNV, 0>(a_mn, b_mn, tmA, tmB, p, st)             \
-                    : launch_major<BNV, 1>(a_mn, b_mn, tmA, tmB, p, st);
+    return elt == 0 ? launch_major<BNV, 0>(a_mn, b_mn, tmA, tmB, tmOut, tmPre, p, st) \
+                    : launch_major<BNV, 1>(a_mn, b_mn, tmA, tmB, tmOut, tmPre, p, st);
   switch (tile_n) {
     KMB_DISPATCH_BN(32)
     KMB_DISPATCH_BN(64)

@@ -89,6 +89,10 @@ class ParamStore:
             for m in grp:
                 dst.append(m)
                 placed.add(m)
+        # the tied embedding / LM-head matrix goes last: its gradient is fully overwritten by the LM-head
+        # wgrad GEMM, everything before it is cleared by one memset and then only accumulated into
+        tail = [n for n in big if n.endswith("shared.weight")]
+        big = [n for n in big if not n.endswith("shared.weight")] + tail
         self.offsets, off = {}, 0
         order = small + big
         for i, n in enumerate(order):
@@ -106,6 +110,7 @@ class ParamStore:
             self.small_end = 0
         self.total = (off + 63) // 64 * 64
         self.big_names = big
+        self.zero_end = self.offsets[tail[0]] if tail else self.total
         self.P = torch.zeros(self.total, dtype=F32, device=self.device)
         self.G = torch.zeros(self.total, dtype=F32, device=self.device)
         self.P16 = torch.zeros(self.total, dtype=BF16, device=self.device)
@@ -510,7 +515,9 @@ class Engine:
         bwd = Plan()
         bwd.stream = a["stream"]
         if not acc:
-            bwd.add(_zero, st.G[:st.small_end])
+            bwd.add(_zero, st.G[:st.zero_end])
+        lm_acc = acc
+        acc = 1   # every other weight gradient accumulates onto the cleared buffer (enables split-K reds)
         gscale = self.buf(a, "ce_gscale", (1,), F32)
         dlog = self.buf(a, "dlogits", (Md, V), BF16)
         dpre_d = [self.buf(a, "g.dpreA_d", (Md, d), F32), self.buf(a, "g.dpreB_d", (Md, d), F32)]
@@ -520,7 +527,7 @@ class Engine:
         self.gemm(bwd, a["dec_b16"], E16, Md, V, d, d, d, tile_n=256, mode=L.EPI_CE_GRAD, bias=a["flb"], labels=a["labels"],
                   ce_lse=a["ce_lse"], ce_gscale=gscale, out_bf16=dlog, ld_bf16=V)
         self.gemm(bwd, dlog, E16, Md, d, V, V, d, b_mn=1, out_bf16=dyb_d)
-        self.gemm(bwd, dlog, a["dec_b16"], V, d, Md, V, d, a_mn=1, b_mn=1, out_f32=st.g(self.n("shared.weight")), ld_f32=d, accumulate=acc)
+        self.gemm(bwd, dlog, a["dec_b16"], V, d, Md, V, d, a_mn=1, b_mn=1, out_f32=st.g(self.n("shared.weight")), ld_f32=d, accumulate=lm_acc)
         # decoder layers, last to first
         dyA, dyB, flip = None, dyb_d, 0
         denc = self.buf(a, "g.denc", (Me, d), F32)

@@ -67,7 +67,9 @@ static int run_case(int M, int N, int K, int a_mn, int b_mn, int elt, int tile_n
 
   KmbGemmEpilogue e; memset(&e, 0, sizeof e);
   e.mode = KMB_EPI_LINEAR; e.alpha = 1.f; e.out_f32 = dOut; e.ld_f32 = N;
-  if (with_epi) { e.bias = dBias; e.residual = dRes; e.ld_res = N; e.alpha = 0.5f; if (N % 8 == 0) { e.out_bf16 = dOutB; e.ld_bf16 = N; } }
+  if (with_epi == 1) { e.bias = dBias; e.residual = dRes; e.ld_res = N; e.alpha = 0.5f; if (N % 8 == 0) { e.out_bf16 = dOutB; e.ld_bf16 = N; } }
+  if (with_epi == 2) { e.accumulate = 1; CK(cudaMemcpy(dOut, hRes.data(), (size_t)M * N * 4, cudaMemcpyHostToDevice)); }   // split-K path
+  if (with_epi == 3) { e.out_f32 = nullptr; e.out_bf16 = dOutB; e.ld_bf16 = N; e.bias = dBias; }                          // TMA-store path
   int rc = kmb_gemm(dA, dB, M, N, K, lda, ldb, a_mn, b_mn, elt, &e, tile_n, 0);
   cudaError_t se = cudaDeviceSynchronize();
   int fail = 0;
@@ -79,16 +81,23 @@ static int run_case(int M, int N, int K, int a_mn, int b_mn, int elt, int tile_n
     std::vector<float> ref((size_t)M * N), out((size_t)M * N);
     CK(cudaMemcpy(ref.data(), dRef, ref.size() * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(out.data(), dOut, out.size() * 4, cudaMemcpyDeviceToHost));
+    if (with_epi == 3) {
+      std::vector<__nv_bfloat16> ob((size_t)M * N);
+      CK(cudaMemcpy(ob.data(), dOutB, ob.size() * 2, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < ob.size(); ++i) out[i] = __bfloat162float(ob[i]);
+    }
     double maxerr = 0, maxref = 0; int nbad = 0;
     for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) {
       float r = ref[(size_t)m * N + n];
-      if (with_epi) r = 0.5f * r + hBias[n] + hRes[(size_t)m * N + n];
+      if (with_epi == 1) r = 0.5f * r + hBias[n] + hRes[(size_t)m * N + n];
+      if (with_epi == 2) r = r + hRes[(size_t)m * N + n];
+      if (with_epi == 3) r = r + hBias[n];
       float o = out[(size_t)m * N + n];
       double err = fabs((double)r - o);
       if (!(err <= 1e30)) err = 1e30;
       if (err > maxerr) maxerr = err;
       if (fabs(r) > maxref) maxref = fabs(r);
-      const double tol = (elt == 0 ? 2e-3 : 2e-3) * sqrt((double)K) + 1e-3;
+      const double tol = (elt == 0 ? 2e-3 : 2e-3) * sqrt((double)K) + 1e-3 + (with_epi == 3 ? 0.01 * fabs(r) : 0.0);
       if (err > tol) { if (nbad < 6) printf("   bad (m=%d,n=%d): ref=%g out=%g\n", m, n, r, o); ++nbad; }
     }
     fail = nbad > 0;
@@ -98,12 +107,18 @@ static int run_case(int M, int N, int K, int a_mn, int b_mn, int elt, int tile_n
   return fail;
 }
 
+__global__ void fill_rand(__nv_bfloat16* p, size_t n, unsigned seed) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) { unsigned x = (unsigned)i * 2654435761u + seed; x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; p[i] = __float2bfloat16(((x & 0xFFFF) / 32768.f - 1.f) * 0.5f); }
+}
+static int g_noout = 0, g_gelu = 0;
 static void bench_case(int M, int N, int K, int a_mn, int b_mn, int tile_n, const char* name) {
   size_t na = (size_t)M * K, nb = (size_t)N * K;
-  __nv_bfloat16 *dA, *dB, *dO;
-  CK(cudaMalloc(&dA, na * 2)); CK(cudaMalloc(&dB, nb * 2)); CK(cudaMalloc(&dO, (size_t)M * N * 2));
-  CK(cudaMemset(dA, 0, na * 2)); CK(cudaMemset(dB, 0, nb * 2));
-  KmbGemmEpilogue e; memset(&e, 0, sizeof e); e.alpha = 1.f; e.out_bf16 = dO; e.ld_bf16 = N;
+  __nv_bfloat16 *dA, *dB, *dO, *dP;
+  CK(cudaMalloc(&dA, na * 2)); CK(cudaMalloc(&dB, nb * 2)); CK(cudaMalloc(&dO, (size_t)M * N * 2)); CK(cudaMalloc(&dP, (size_t)M * N * 2));
+  fill_rand<<<(na + 255) / 256, 256>>>(dA, na, 1); fill_rand<<<(nb + 255) / 256, 256>>>(dB, nb, 2);
+  KmbGemmEpilogue e; memset(&e, 0, sizeof e); e.alpha = 1.f; e.out_bf16 = g_noout ? nullptr : dO; e.ld_bf16 = N;
+  if (g_gelu) { e.act = KMB_ACT_GELU; e.out_preact = dP; }
   const int lda = a_mn ? M : K, ldb = b_mn ? N : K;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; ++i) kmb_gemm(dA, dB, M, N, K, lda, ldb, a_mn, b_mn, 0, &e, tile_n, 0);
@@ -113,7 +128,7 @@ static void bench_case(int M, int N, int K, int a_mn, int b_mn, int tile_n, cons
   cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
   printf("BENCH %-12s M=%d N=%d K=%d mn=%d%d tile_n=%d: %.3f ms  %.1f TFLOP/s\n", name, M, N, K, a_mn, b_mn, tile_n, ms, 2.0 * M * N * K / ms / 1e9);
-  cudaFree(dA); cudaFree(dB); cudaFree(dO);
+  cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dP);
 }
 
 int main(int argc, char** argv) {
@@ -133,9 +148,31 @@ int main(int argc, char** argv) {
     fails += run_case(256, 256, 96, amn, bmn, 1, 128, 0);   // tf32
     fails += run_case(200, 136, 100, amn, bmn, 1, 0, 1);    // tf32 ragged
   }
+  fails += run_case(256, 512, 8192, 1, 1, 0, 0, 2);    // split-K reds
+  fails += run_case(768, 768, 12800, 1, 1, 0, 0, 2);
+  fails += run_case(200, 328, 4000, 1, 1, 0, 128, 2);
+  fails += run_case(1000, 520, 200, 0, 0, 0, 256, 3);  // TMA-store epilogue with ragged M / N
+  fails += run_case(1000, 520, 200, 0, 1, 0, 128, 3);
+  fails += run_case(300, 72, 200, 0, 0, 0, 64, 3);
   fails += run_case(4096, 768, 768, 0, 0, 0, 0, 1);   // many tiles per CTA (pipeline wrap)
   fails += run_case(20000, 256, 64, 0, 0, 0, 128, 0); // > 148 tiles with 1 k-block
   printf("gemm_test: %d failing case(s)\n", fails);
+  if (argc > 1 && !strcmp(argv[1], "bench2")) {
+    for (int mode = 0; mode < 3; ++mode) {
+      g_noout = mode == 0; g_gelu = mode == 2;
+      printf("--- mode %s\n", mode == 0 ? "no output (mainloop bound)" : mode == 1 ? "bf16 out" : "gelu + preact + bf16 out");
+      for (int tn : {128, 256}) {
+        bench_case(12800, 768, 768, 0, 0, tn, "proj");
+        bench_case(12800, 2304, 768, 0, 0, tn, "qkv");
+        bench_case(12800, 3072, 768, 0, 0, tn, "fc1");
+        bench_case(12800, 768, 3072, 0, 0, tn, "fc2");
+        bench_case(12800, 768, 3072, 0, 1, tn, "dgrad_fc1");
+        bench_case(768, 3072, 12800, 1, 1, tn, "wgrad_fc2");
+      }
+    }
+    bench_case(8192, 8192, 8192, 0, 0, 256, "big");
+    return 0;
+  }
   if (argc > 1 && !strcmp(argv[1], "bench")) {
     bench_case(12800, 768, 768, 0, 0, 0, "proj");
     bench_case(12800, 768, 768, 0, 0, 128, "proj128");
