@@ -18,7 +18,8 @@
 namespace kmb {
 
 constexpr int TQ = 64;   // rows owned by a CTA (4 warps x 16)
-constexpr int TK = 64;   // streamed block
+constexpr int TK = 64;   // key / query block of one MMA pass
+constexpr int SB = 128;  // rows of the streamed operand resident in shared memory at a time
 constexpr int DH = 64;
 constexpr int LDS = 72;  // padded smem row (elements) -> conflict-free ldmatrix
 
@@ -73,6 +74,24 @@ __device__ __forceinline__ void load_tile(bf16* s, const bf16* g, int64_t ld, in
   }
 }
 
+// Asynchronous variant (cp.async, 16 B per request, zero-fill past nrows): `rows` rows starting at r0.
+// All tiles a CTA needs are requested up front and awaited once, so a CTA has a single exposed
+// global-memory latency instead of one per tile.
+__device__ __forceinline__ void load_tile_async(bf16* s, const bf16* g, int64_t ld, int r0, int nrows, int rows) {
+  for (int i = threadIdx.x; i < rows * 8; i += blockDim.x) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    const bool ok = (r0 + r) < nrows;
+    const bf16* src = ok ? g + (int64_t)(r0 + r) * ld + c : g;
+    const uint32_t dst = smem_u32(s + r * LDS + c);
+    const int sz = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // A-operand fragments (16 rows x 64) for this warp's rows
 __device__ __forceinline__ void load_a_frags(uint32_t (&f)[4][4], const bf16* s, int warp, int lane) {
 #pragma unroll
@@ -125,19 +144,17 @@ __device__ __forceinline__ void store_rows(bf16* g, int64_t ld, int r_lo, int nr
 
 // ------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
-  __shared__ __align__(16) bf16 sQ[TQ * LDS];
-  __shared__ __align__(16) bf16 sK[TK * LDS];
-  __shared__ __align__(16) bf16 sV[TK * LDS];
-  __shared__ uint8_t sPad[TK];
+  extern __shared__ __align__(16) uint8_t dsm[];
+  bf16* sQ = reinterpret_cast<bf16*>(dsm);
+  bf16* sK = sQ + TQ * LDS;
+  bf16* sV = sK + SB * LDS;
+  uint8_t* sPad = reinterpret_cast<uint8_t*>(sV + SB * LDS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
   const bf16* qg = p.q + b * p.sbq + h * p.shq;
   const bf16* kg = p.k + b * p.sbk + h * p.shk;
   const bf16* vg = p.v + b * p.sbv + h * p.shv;
-  load_tile(sQ, qg, p.ldq, q0, p.Sq);
-  __syncthreads();
   uint32_t qf[4][4];
-  load_a_frags(qf, sQ, warp, lane);
   float o[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
@@ -145,52 +162,61 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
   const int r_lo = q0 + warp * 16 + g;
   int kend = p.Sk;
   if (p.causal && q0 + TQ < kend) kend = q0 + TQ;
-  for (int k0 = 0; k0 < kend; k0 += TK) {
+  for (int kk0 = 0; kk0 < kend; kk0 += SB) {
     __syncthreads();
-    load_tile(sK, kg, p.ldk, k0, p.Sk);
-    load_tile(sV, vg, p.ldv, k0, p.Sk);
-    if (threadIdx.x < TK) {
-      const int c = k0 + threadIdx.x;
+    if (kk0 == 0) load_tile_async(sQ, qg, p.ldq, q0, p.Sq, TQ);
+    load_tile_async(sK, kg, p.ldk, kk0, p.Sk, SB);
+    load_tile_async(sV, vg, p.ldv, kk0, p.Sk, SB);
+    if (threadIdx.x < SB) {
+      const int c = kk0 + threadIdx.x;
       sPad[threadIdx.x] = (c >= p.Sk) ? 1 : (p.key_pad ? p.key_pad[(int64_t)b * p.Sk + c] : 0);
     }
+    cp_async_wait_all();
     __syncthreads();
-    float s[8][4];
+    if (kk0 == 0) load_a_frags(qf, sQ, warp, lane);
+    const int kstop = min(kend, kk0 + SB);
+    for (int k0 = kk0; k0 < kstop; k0 += TK) {
+      const bf16* sKb = sK + (k0 - kk0) * LDS;
+      const bf16* sVb = sV + (k0 - kk0) * LDS;
+      const uint8_t* sPb = sPad + (k0 - kk0);
+      float s[8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-    mma_a_yt(s, qf, sK, lane);
-    float mx[2] = {-INFINITY, -INFINITY};
+      for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+      mma_a_yt(s, qf, sKb, lane);
+      float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int cl = nt * 8 + 2 * t + (e & 1);
-        const int row = r_lo + (e >> 1) * 8;
-        const bool masked = sPad[cl] || (p.causal && (k0 + cl) > row);
-        const float v = masked ? -INFINITY : s[nt][e] * p.scale;
-        s[nt][e] = v;
-        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+        for (int e = 0; e < 4; ++e) {
+          const int cl = nt * 8 + 2 * t + (e & 1);
+          const int row = r_lo + (e >> 1) * 8;
+          const bool masked = sPb[cl] || (p.causal && (k0 + cl) > row);
+          const float v = masked ? -INFINITY : s[nt][e] * p.scale;
+          s[nt][e] = v;
+          mx[e >> 1] = fmaxf(mx[e >> 1], v);
+        }
+      float corr[2], mnew[2];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+        mnew[hh] = fmaxf(mrow[hh], mx[hh]);
+        corr[hh] = (mnew[hh] == -INFINITY) ? 1.f : __expf(mrow[hh] - mnew[hh]);
+        mrow[hh] = mnew[hh];
+        lrow[hh] *= corr[hh];
       }
-    float corr[2], mnew[2];
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
-      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
-      mnew[hh] = fmaxf(mrow[hh], mx[hh]);
-      corr[hh] = (mnew[hh] == -INFINITY) ? 1.f : __expf(mrow[hh] - mnew[hh]);
-      mrow[hh] = mnew[hh];
-      lrow[hh] *= corr[hh];
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int hh = e >> 1;
+          const float pv = (mnew[hh] == -INFINITY) ? 0.f : __expf(s[nt][e] - mnew[hh]);
+          s[nt][e] = pv;
+          lrow[hh] += pv;
+          o[nt][e] *= corr[hh];
+        }
+      mma_p_y(o, s, sVb, lane);
     }
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int hh = e >> 1;
-        const float pv = (mnew[hh] == -INFINITY) ? 0.f : __expf(s[nt][e] - mnew[hh]);
-        s[nt][e] = pv;
-        lrow[hh] += pv;
-        o[nt][e] *= corr[hh];
-      }
-    mma_p_y(o, s, sV, lane);
   }
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
@@ -225,10 +251,12 @@ __global__ void attn_bwd_prep_kernel(const AttnParams p) {
 
 // ------------------------------------------------------------------ backward, query-row owner: dQ
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
-  __shared__ __align__(16) bf16 sX[TQ * LDS];  // Q then dO (fragments are kept in registers)
-  __shared__ __align__(16) bf16 sK[TK * LDS];
-  __shared__ __align__(16) bf16 sV[TK * LDS];
-  __shared__ uint8_t sPad[TK];
+  extern __shared__ __align__(16) uint8_t dsm[];
+  bf16* sQ = reinterpret_cast<bf16*>(dsm);
+  bf16* sdO = sQ + TQ * LDS;
+  bf16* sK = sdO + TQ * LDS;
+  bf16* sV = sK + SB * LDS;
+  uint8_t* sPad = reinterpret_cast<uint8_t*>(sV + SB * LDS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
   const bf16* qg = p.q + b * p.sbq + h * p.shq;
@@ -236,13 +264,6 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
   const bf16* vg = p.v + b * p.sbv + h * p.shv;
   const bf16* dog = p.dO + (int64_t)b * p.Sq * p.lddo + h * DH;
   uint32_t qf[4][4], dof[4][4];
-  load_tile(sX, qg, p.ldq, q0, p.Sq);
-  __syncthreads();
-  load_a_frags(qf, sX, warp, lane);
-  __syncthreads();
-  load_tile(sX, dog, p.lddo, q0, p.Sq);
-  __syncthreads();
-  load_a_frags(dof, sX, warp, lane);
   const int r_lo = q0 + warp * 16 + g;
   const float* lse = p.lse + ((int64_t)b * p.H + h) * p.Sq;
   const float* Dg = p.D + ((int64_t)b * p.H + h) * p.Sq;
@@ -256,35 +277,50 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
   for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
   int kend = p.Sk;
   if (p.causal && q0 + TQ < kend) kend = q0 + TQ;
-  for (int k0 = 0; k0 < kend; k0 += TK) {
+  for (int kk0 = 0; kk0 < kend; kk0 += SB) {
     __syncthreads();
-    load_tile(sK, kg, p.ldk, k0, p.Sk);
-    load_tile(sV, vg, p.ldv, k0, p.Sk);
-    if (threadIdx.x < TK) {
-      const int c = k0 + threadIdx.x;
+    if (kk0 == 0) {
+      load_tile_async(sQ, qg, p.ldq, q0, p.Sq, TQ);
+      load_tile_async(sdO, dog, p.lddo, q0, p.Sq, TQ);
+    }
+    load_tile_async(sK, kg, p.ldk, kk0, p.Sk, SB);
+    load_tile_async(sV, vg, p.ldv, kk0, p.Sk, SB);
+    if (threadIdx.x < SB) {
+      const int c = kk0 + threadIdx.x;
       sPad[threadIdx.x] = (c >= p.Sk) ? 1 : (p.key_pad ? p.key_pad[(int64_t)b * p.Sk + c] : 0);
     }
+    cp_async_wait_all();
     __syncthreads();
-    float s[8][4], dp[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-      dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+    if (kk0 == 0) {
+      load_a_frags(qf, sQ, warp, lane);
+      load_a_frags(dof, sdO, warp, lane);
     }
-    mma_a_yt(s, qf, sK, lane);
-    mma_a_yt(dp, dof, sV, lane);
+    const int kstop = min(kend, kk0 + SB);
+    for (int k0 = kk0; k0 < kstop; k0 += TK) {
+      const bf16* sKb = sK + (k0 - kk0) * LDS;
+      const bf16* sVb = sV + (k0 - kk0) * LDS;
+      const uint8_t* sPb = sPad + (k0 - kk0);
+      float s[8][4], dp[8][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int cl = nt * 8 + 2 * t + (e & 1);
-        const int hh = e >> 1;
-        const int row = r_lo + hh * 8;
-        const bool masked = sPad[cl] || (p.causal && (k0 + cl) > row) || lrow[hh] == -INFINITY;
-        const float pv = masked ? 0.f : __expf(s[nt][e] * p.scale - lrow[hh]);
-        s[nt][e] = pv * (dp[nt][e] - drow[hh]) * p.scale;  // dS
+      for (int i = 0; i < 8; ++i) {
+        s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+        dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
       }
-    mma_p_y(dq, s, sK, lane);
+      mma_a_yt(s, qf, sKb, lane);
+      mma_a_yt(dp, dof, sVb, lane);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int cl = nt * 8 + 2 * t + (e & 1);
+          const int hh = e >> 1;
+          const int row = r_lo + hh * 8;
+          const bool masked = sPb[cl] || (p.causal && (k0 + cl) > row) || lrow[hh] == -INFINITY;
+          const float pv = masked ? 0.f : __expf(s[nt][e] * p.scale - lrow[hh]);
+          s[nt][e] = pv * (dp[nt][e] - drow[hh]) * p.scale;  // dS
+        }
+      mma_p_y(dq, s, sKb, lane);
+    }
   }
   bf16* dqg = p.dq + (int64_t)b * p.Sq * p.lddq + h * DH;
   store_rows(dqg, p.lddq, r_lo, p.Sq, dq, lane, 1.f, 1.f);
@@ -292,10 +328,13 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
 
 // ------------------------------------------------------------------ backward, key-row owner: dK, dV
 __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnParams p) {
-  __shared__ __align__(16) bf16 sX[TK * LDS];  // K then V of the owned rows
-  __shared__ __align__(16) bf16 sQ[TQ * LDS];
-  __shared__ __align__(16) bf16 sdO[TQ * LDS];
-  __shared__ float sL[TQ], sD[TQ];
+  extern __shared__ __align__(16) uint8_t dsm[];
+  bf16* sKr = reinterpret_cast<bf16*>(dsm);  // owned key rows: K and V
+  bf16* sVr = sKr + TK * LDS;
+  bf16* sQ = sVr + TK * LDS;                  // streamed query rows: Q and dO
+  bf16* sdO = sQ + SB * LDS;
+  float* sL = reinterpret_cast<float*>(sdO + SB * LDS);
+  float* sD = sL + SB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int k0 = blockIdx.x * TK, h = blockIdx.y, b = blockIdx.z;
   const bf16* qg = p.q + b * p.sbq + h * p.shq;
@@ -305,13 +344,6 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnParams p) {
   const float* lse = p.lse + ((int64_t)b * p.H + h) * p.Sq;
   const float* Dg = p.D + ((int64_t)b * p.H + h) * p.Sq;
   uint32_t kf[4][4], vf[4][4];
-  load_tile(sX, kg, p.ldk, k0, p.Sk);
-  __syncthreads();
-  load_a_frags(kf, sX, warp, lane);
-  __syncthreads();
-  load_tile(sX, vg, p.ldv, k0, p.Sk);
-  __syncthreads();
-  load_a_frags(vf, sX, warp, lane);
   const int r_lo = k0 + warp * 16 + g;  // key index of this thread's rows
   bool rpad[2];
 #pragma unroll
@@ -326,45 +358,79 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnParams p) {
     dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
   }
   const int qstart = p.causal ? (k0 / TQ) * TQ : 0;  // queries before the key block see none of it
-  for (int q0 = qstart; q0 < p.Sq; q0 += TQ) {
+  for (int qq0 = qstart; qq0 < p.Sq; qq0 += SB) {
     __syncthreads();
-    load_tile(sQ, qg, p.ldq, q0, p.Sq);
-    load_tile(sdO, dog, p.lddo, q0, p.Sq);
-    if (threadIdx.x < TQ) {
-      const int r = q0 + threadIdx.x;
+    if (qq0 == qstart) {
+      load_tile_async(sKr, kg, p.ldk, k0, p.Sk, TK);
+      load_tile_async(sVr, vg, p.ldv, k0, p.Sk, TK);
+    }
+    load_tile_async(sQ, qg, p.ldq, qq0, p.Sq, SB);
+    load_tile_async(sdO, dog, p.lddo, qq0, p.Sq, SB);
+    if (threadIdx.x < SB) {
+      const int r = qq0 + threadIdx.x;
       sL[threadIdx.x] = r < p.Sq ? lse[r] : -INFINITY;
       sD[threadIdx.x] = r < p.Sq ? Dg[r] : 0.f;
     }
+    cp_async_wait_all();
     __syncthreads();
-    float st[8][4], dpt[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
-      dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
+    if (qq0 == qstart) {
+      load_a_frags(kf, sKr, warp, lane);
+      load_a_frags(vf, sVr, warp, lane);
     }
-    mma_a_yt(st, kf, sQ, lane);     // S^T = K Q^T
-    mma_a_yt(dpt, vf, sdO, lane);   // dP^T = V dO^T
-    float ds[8][4];
+    const int qstop = min(p.Sq, qq0 + SB);
+    for (int q0 = qq0; q0 < qstop; q0 += TQ) {
+      const bf16* sQb = sQ + (q0 - qq0) * LDS;
+      const bf16* sdOb = sdO + (q0 - qq0) * LDS;
+      const float* sLb = sL + (q0 - qq0);
+      const float* sDb = sD + (q0 - qq0);
+      float st[8][4], dpt[8][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int cl = nt * 8 + 2 * t + (e & 1);  // query within block
-        const int hh = e >> 1;
-        const int key = r_lo + hh * 8;
-        const float l = sL[cl];
-        const bool masked = rpad[hh] || l == -INFINITY || (p.causal && key > (q0 + cl));
-        const float pv = masked ? 0.f : __expf(st[nt][e] * p.scale - l);
-        st[nt][e] = pv;                                        // P^T
-        ds[nt][e] = pv * (dpt[nt][e] - sD[cl]) * p.scale;      // dS^T
+      for (int i = 0; i < 8; ++i) {
+        st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+        dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
       }
-    mma_p_y(dv, st, sdO, lane);
-    mma_p_y(dk, ds, sQ, lane);
+      mma_a_yt(st, kf, sQb, lane);     // S^T = K Q^T
+      mma_a_yt(dpt, vf, sdOb, lane);   // dP^T = V dO^T
+      float ds[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int cl = nt * 8 + 2 * t + (e & 1);  // query within block
+          const int hh = e >> 1;
+          const int key = r_lo + hh * 8;
+          const float l = sLb[cl];
+          const bool masked = rpad[hh] || l == -INFINITY || (p.causal && key > (q0 + cl));
+          const float pv = masked ? 0.f : __expf(st[nt][e] * p.scale - l);
+          st[nt][e] = pv;                                        // P^T
+          ds[nt][e] = pv * (dpt[nt][e] - sDb[cl]) * p.scale;     // dS^T
+        }
+      mma_p_y(dv, st, sdOb, lane);
+      mma_p_y(dk, ds, sQb, lane);
+    }
   }
   bf16* dkg = p.dk + (int64_t)b * p.Sk * p.lddk + h * DH;
   bf16* dvg = p.dv + (int64_t)b * p.Sk * p.lddv + h * DH;
   store_rows(dkg, p.lddk, r_lo, p.Sk, dk, lane, 1.f, 1.f);
   store_rows(dvg, p.lddv, r_lo, p.Sk, dv, lane, 1.f, 1.f);
+}
+
+constexpr int SMEM_FWD = (TQ + 2 * SB) * LDS * 2 + SB;
+constexpr int SMEM_DQ = (2 * TQ + 2 * SB) * LDS * 2 + SB;
+constexpr int SMEM_DKV = (2 * TK + 2 * SB) * LDS * 2 + 2 * SB * 4;
+
+static int set_attn_smem_attrs() {
+  static bool done = false;
+  if (done) return KMB_OK;
+  cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV);
+  if (e != cudaSuccess) {
+    kmb_set_last_error(cudaGetErrorString(e), __FILE__, __LINE__);
+    return KMB_ERR_CUDA;
+  }
+  done = true;
+  return KMB_OK;
 }
 
 static int check_attn_args(const AttnParams& p) {
@@ -396,7 +462,8 @@ extern "C" int kmb_attn_fwd(const void* q, const void* k, const void* v, int64_t
     return KMB_ERR_ARG;
   }
   dim3 grid((Sq + TQ - 1) / TQ, H, B);
-  attn_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+  if (set_attn_smem_attrs()) return KMB_ERR_CUDA;
+  attn_fwd_kernel<<<grid, 128, SMEM_FWD, (cudaStream_t)stream>>>(p);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }
@@ -418,7 +485,8 @@ extern "C" int kmb_attn_fwd_strided(const void* q, const void* k, const void* v,
   for (int i = 0; i < 12; ++i) bad = bad || (strides12[i] % 8);
   if (bad) { kmb_set_last_error("kmb_attn_fwd_strided: bad argument", __FILE__, __LINE__); return KMB_ERR_ARG; }
   dim3 grid((Sq + TQ - 1) / TQ, H, B);
-  attn_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+  if (set_attn_smem_attrs()) return KMB_ERR_CUDA;
+  attn_fwd_kernel<<<grid, 128, SMEM_FWD, (cudaStream_t)stream>>>(p);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }
@@ -445,9 +513,10 @@ extern "C" int kmb_attn_bwd(const void* q, const void* k, const void* v, int64_t
   const int rows = B * H * Sq;
   attn_bwd_prep_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>(p);
   KMB_CHECK_LAUNCH();
-  attn_bwd_dq_kernel<<<dim3((Sq + TQ - 1) / TQ, H, B), 128, 0, st>>>(p);
+  if (set_attn_smem_attrs()) return KMB_ERR_CUDA;
+  attn_bwd_dq_kernel<<<dim3((Sq + TQ - 1) / TQ, H, B), 128, SMEM_DQ, st>>>(p);
   KMB_CHECK_LAUNCH();
-  attn_bwd_dkv_kernel<<<dim3((Sk + TK - 1) / TK, H, B), 128, 0, st>>>(p);
+  attn_bwd_dkv_kernel<<<dim3((Sk + TK - 1) / TK, H, B), 128, SMEM_DKV, st>>>(p);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }

@@ -745,7 +745,13 @@ extern "C" int kmb_gemm(const void* A, const void* B, int M, int N, int K, int64
     kmb_set_last_error("kmb_gemm: operands must be 16-byte aligned with 16-byte row pitch", __FILE__, __LINE__);
     return KMB_ERR_ARG;
   }
-  if (tile_n == 0) tile_n = kmb_gemm_pick_tile_n(M, N);
+  const bool splitk_ok = epi->mode == KMB_EPI_LINEAR && epi->accumulate && epi->out_f32 && !epi->out_bf16 &&
+                         !epi->residual && !epi->bias && epi->act == KMB_ACT_NONE && epi->dropout_p <= 0.f;
+  if (tile_n == 0) {
+    // split-K fills the SMs for weight-gradient shapes, so they can always use the widest tile
+    if (splitk_ok) tile_n = N > 128 ? 256 : (N > 64 ? 128 : 64);
+    else tile_n = kmb_gemm_pick_tile_n(M, N);
+  }
   if (tile_n != 32 && tile_n != 64 && tile_n != 128 && tile_n != 256) {
     kmb_set_last_error("kmb_gemm: tile_n must be 32/64/128/256", __FILE__, __LINE__);
     return KMB_ERR_ARG;
@@ -798,8 +804,7 @@ extern "C" int kmb_gemm(const void* A, const void* B, int M, int N, int K, int64
   // split-K: weight-gradient shaped problems (few output tiles, long K) that accumulate into fp32
   p.split_k = 1;
   p.kb_per_split = p.k_blocks;
-  if (epi->mode == KMB_EPI_LINEAR && epi->accumulate && epi->out_f32 && !epi->out_bf16 && !epi->residual && !epi->bias &&
-      epi->act == KMB_ACT_NONE && epi->dropout_p <= 0.f) {
+  if (splitk_ok) {
     const int tiles = p.m_tiles * p.n_tiles;
     const int sms = num_sms();
     int best = 1;

@@ -602,8 +602,9 @@ extern "C" int kmb_layernorm_bwd(const float* dy, const void* dy_bf16, const flo
     kmb_set_last_error("kmb_layernorm_bwd: d_model must be a multiple of 4 and <= 1024", __FILE__, __LINE__);
     return KMB_ERR_ARG;
   }
-  // ~148 SMs x 8 resident blocks; at least LN_RB rows per block so the statistics batch is full
-  int rows_per_block = (M + 148 * 8 - 1) / (148 * 8);
+  // ~3 blocks per SM: enough loads in flight to saturate HBM while keeping the number of per-block
+  // column-sum atomics (3*d per block) small
+  int rows_per_block = (M + 148 * 3 - 1) / (148 * 3);
   rows_per_block = (rows_per_block + LN_RB - 1) / LN_RB * LN_RB;
   if (rows_per_block < 2 * LN_RB) rows_per_block = 2 * LN_RB;
   const int blocks = (M + rows_per_block - 1) / rows_per_block;
