@@ -220,30 +220,42 @@ __host__ __device__ __forceinline__ bool dropout_keep(uint64_t bits4, int lane, 
 }
 
 // exact-erf GELU (HF-3.0.2 ACT2FN["gelu"] = F.gelu).  erf via Abramowitz-Stegun 7.1.26
-// (|abs err| <= 1.5e-7, far below the bf16 rounding applied to every result); the exp(-x^2/2)
-// it needs is the Gaussian pdf the derivative also needs, so forward and backward cost one
-// MUFU.EX2 and one MUFU.RCP per element.
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  const float e = __expf(-z * z);  // = exp(-x^2 / 2)
+// (|abs err| <= 1.5e-7 plus MUFU approximation error ~1e-6, far below the bf16 rounding applied to
+// every result).  With a = |x|, t = 1/(1 + p a/sqrt2), q = t*poly(t), e = exp(-x^2/2):
+//   erf(a/sqrt2) = 1 - q e      gelu(x)  = max(x,0) - 0.5 a q e
+//                               gelu'(x) = 0.5 + sign(x) 0.5 (1 - q e) + x e / sqrt(2 pi)
+// One MUFU.RCP + one MUFU.EX2 and ~12 FP32 ops per element; the epilogue of the fc1 GEMM is
+// issue-bound on exactly this code, so every instruction counts.
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void gelu_qe(float x, float& a, float& qe, float& e) {
+  a = fabsf(x);
+  const float t = fast_rcp(fmaf(0.23164189f, a, 1.0f));    // 0.3275911 / sqrt(2)
+  e = fast_ex2(a * a * -0.72134752044f);                    // exp(-x^2/2) = 2^(-x^2 * log2(e)/2)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = fmaf(-poly * t, e, 1.0f);
-  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
-  pdf = 0.39894228040143267794f * e;
+  qe = poly * t * e;
 }
 __device__ __forceinline__ float gelu_erf(float x) {
-  float cdf, pdf;
-  gelu_parts(x, cdf, pdf);
-  return x * cdf;
+  float a, qe, e;
+  gelu_qe(x, a, qe, e);
+  return fmaf(-0.5f * a, qe, fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf, pdf;
-  gelu_parts(x, cdf, pdf);
-  return fmaf(x, pdf, cdf);
+  float a, qe, e;
+  gelu_qe(x, a, qe, e);
+  const float half_erf = copysignf(fmaf(-0.5f, qe, 0.5f), x);
+  return fmaf(x * 0.39894228040143267794f, e, 0.5f + half_erf);
 }
 
 // ---------------------------------------------------------------- TMA store (smem -> global)

@@ -133,6 +133,12 @@ static void bench_case(int M, int N, int K, int a_mn, int b_mn, int tile_n, cons
 
 int main(int argc, char** argv) {
   if (kmb_arch_check() != 0) { printf("arch check failed: %s\n", kmb_last_error()); return 97; }
+  if (argc > 2 && !strcmp(argv[1], "one")) {   // single shape for ncu: one <mode 0|1|2>
+    const int mode = atoi(argv[2]);
+    g_noout = mode == 0; g_gelu = mode == 2;
+    bench_case(12800, 3072, 768, 0, 0, 256, "fc1");
+    return 0;
+  }
   int fails = 0;
   srand(1);
   // smallest possible first: one tile, one k-block, K-major both
