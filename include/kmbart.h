@@ -50,7 +50,8 @@ const char* kmb_last_error(void);
  * Operand storage: a_mn = 0 -> A is stored [M, lda] with k contiguous ("K-major");
  *                  a_mn = 1 -> A is stored [K, lda] with m contiguous ("MN-major").
  *                  Same for B with n.  elt = 0: bf16 operands; elt = 1: fp32 operands
- *                  consumed as tf32.  Accumulation is fp32 in tensor memory.
+ *                  consumed as tf32 (K-major only; with kmb_split_tf32 operands this is the
+ *                  3xTF32 fp32-parity mode).  Accumulation is fp32 in tensor memory.
  * Epilogue modes:
  *   KMB_EPI_LINEAR   v = alpha*acc (+bias[n]) ; act ; dropout ; (+residual) ; (+= out_f32)
  *                    then written to out_f32 and/or out_bf16.
@@ -200,12 +201,15 @@ int kmb_small_xent(const float* logits, int64_t ld, int n, int C, int mode, cons
  *   vcg_train.py:100 / pretrain.py:100, stepped at src/training.py:136-143).
  * table_dev: device array of {float* p; const float* g; float* m; float* v; bf16* p16;
  * int64 n}; chunk_map_dev: device array of int2 {tensor, chunk}; chunks are
- * kmb_adamw_chunk_elems() elements.  step_dev is incremented on device (graph-replay
- * safe).  p16 (optional) receives the refreshed bf16 shadow weights.
+ * kmb_adamw_chunk_elems() elements.  step_dev points at TWO 32-bit words {int step; float
+ * step_size}: the step is incremented and the bias-corrected step size is recomputed (in
+ * double, like the Python reference) on device, so the call is graph-replay safe.  p16
+ * (optional) receives the refreshed bf16 shadow weights.  Hyper-parameters are doubles
+ * because the reference derives 1-beta and beta^t in Python floats.
  */
 int kmb_adamw_chunk_elems(void);
-int kmb_adamw_multi(const void* table_dev, const void* chunk_map_dev, int n_chunks, int* step_dev, float lr,
-                    float beta1, float beta2, float eps, float weight_decay, int correct_bias,
+int kmb_adamw_multi(const void* table_dev, const void* chunk_map_dev, int n_chunks, int* step_dev, double lr,
+                    double beta1, double beta2, double eps, double weight_decay, int correct_bias,
                     const float* inv_scale_dev, kmb_stream_t stream);
 int kmb_cast_bf16(const float* src, void* dst, int64_t n, kmb_stream_t stream);
 int kmb_repack_img_weight(const float* w, void* w_feat_bf16, float* w_box, int d, int fin, kmb_stream_t stream);

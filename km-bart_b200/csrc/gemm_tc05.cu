@@ -740,6 +740,11 @@ extern "C" int kmb_gemm(const void* A, const void* B, int M, int N, int K, int64
     kmb_set_last_error("kmb_gemm: bad argument", __FILE__, __LINE__);
     return KMB_ERR_ARG;
   }
+  if (elt == 1 && (a_mn || b_mn)) {
+    // only the forward (parity-mode) GEMMs run in tf32 and both of their operands are K-major
+    kmb_set_last_error("kmb_gemm: tf32 operands must be K-major (a_mn = b_mn = 0)", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
   const int esz = elt == 0 ? 2 : 4;
   if ((lda * esz) % 16 || (ldb * esz) % 16 || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) {
     kmb_set_last_error("kmb_gemm: operands must be 16-byte aligned with 16-byte row pitch", __FILE__, __LINE__);

@@ -112,9 +112,8 @@ __global__ void __launch_bounds__(256) small_xent_kernel(const float* logits, in
 
 // ------------------------------------------------------------------ AdamW (HF-3.0.2 semantics)
 struct AdamHyper {
-  float lr, beta1, beta2, eps, weight_decay;
-  int correct_bias;
-  const int* step;          // device scalar, already incremented for this step
+  float lr, beta1, beta2, omb1, omb2, eps, weight_decay, lr_wd;  // omb = 1 - beta, rounded from double like the reference
+  const int* step;          // device {int step; float step_size}: written by step_incr_kernel for this step
   const float* inv_scale;   // optional device scalar multiplying the gradients (GradScaler), or null
 };
 
@@ -124,23 +123,23 @@ __device__ __forceinline__ void adam_update4(float4& p, float4 g, float4& m, flo
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float gi = gg[i] * gs;
-    mm[i] = h.beta1 * mm[i] + (1.f - h.beta1) * gi;
-    vv[i] = h.beta2 * vv[i] + (1.f - h.beta2) * gi * gi;
+    mm[i] = h.beta1 * mm[i] + h.omb1 * gi;
+    vv[i] = h.beta2 * vv[i] + h.omb2 * gi * gi;
     pp[i] -= step_size * mm[i] / (sqrtf(vv[i]) + h.eps);
-    if (h.weight_decay > 0.f) pp[i] -= h.lr * h.weight_decay * pp[i];
+    if (h.weight_decay > 0.f) pp[i] -= h.lr_wd * pp[i];
   }
 }
 
-__device__ __forceinline__ float adam_step_size(const AdamHyper& h) {
-  float ss = h.lr;
-  if (h.correct_bias) {
-    const float t = (float)(*h.step);
-    ss = h.lr * sqrtf(1.f - powf(h.beta2, t)) / (1.f - powf(h.beta1, t));
-  }
-  return ss;
-}
+__device__ __forceinline__ float adam_step_size(const AdamHyper& h) { return __int_as_float(h.step[1]); }
 
-__global__ void step_incr_kernel(int* step) { *step += 1; }
+// step += 1; step_size = lr * sqrt(1 - beta2^t) / (1 - beta1^t) in double, like the Python reference
+__global__ void step_incr_kernel(int* step, double lr, double beta1, double beta2, int correct_bias) {
+  const int t = *step + 1;
+  *step = t;
+  double ss = lr;
+  if (correct_bias) ss = lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t));
+  step[1] = __float_as_int((float)ss);
+}
 
 struct AdamTensor {
   float* p;
@@ -281,18 +280,19 @@ extern "C" int kmb_small_xent(const float* logits, int64_t ld, int n, int C, int
 
 extern "C" int kmb_adamw_chunk_elems(void) { return ADAM_CHUNK; }
 
-extern "C" int kmb_adamw_multi(const void* table_dev, const void* chunk_map_dev, int n_chunks, int* step_dev, float lr,
-                               float beta1, float beta2, float eps, float weight_decay, int correct_bias,
+extern "C" int kmb_adamw_multi(const void* table_dev, const void* chunk_map_dev, int n_chunks, int* step_dev, double lr,
+                               double beta1, double beta2, double eps, double weight_decay, int correct_bias,
                                const float* inv_scale_dev, kmb_stream_t stream) {
   if (!table_dev || !chunk_map_dev || n_chunks <= 0 || !step_dev) {
     kmb_set_last_error("kmb_adamw_multi: bad argument", __FILE__, __LINE__);
     return KMB_ERR_ARG;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  step_incr_kernel<<<1, 1, 0, st>>>(step_dev);
+  step_incr_kernel<<<1, 1, 0, st>>>(step_dev, lr, beta1, beta2, correct_bias);
   AdamHyper h;
-  h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay;
-  h.correct_bias = correct_bias; h.step = step_dev; h.inv_scale = inv_scale_dev;
+  h.lr = (float)lr; h.beta1 = (float)beta1; h.beta2 = (float)beta2; h.omb1 = (float)(1.0 - beta1); h.omb2 = (float)(1.0 - beta2);
+  h.eps = (float)eps; h.weight_decay = (float)weight_decay; h.lr_wd = (float)(lr * weight_decay);
+  h.step = step_dev; h.inv_scale = inv_scale_dev;
   adamw_multi_kernel<<<n_chunks, 256, 0, st>>>((const AdamTensor*)table_dev, (const int2*)chunk_map_dev, h);
   KMB_CHECK_LAUNCH();
   return KMB_OK;

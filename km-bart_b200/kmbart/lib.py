@@ -62,7 +62,7 @@ _PROTOS = {
     "kmb_small_xent": [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_float, c_void_p,
                        c_void_p, c_int64, c_void_p, c_void_p],
     "kmb_adamw_chunk_elems": [],
-    "kmb_adamw_multi": [c_void_p, c_void_p, c_int, c_void_p, c_float, c_float, c_float, c_float, c_float, c_int,
+    "kmb_adamw_multi": [c_void_p, c_void_p, c_int, c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_int,
                         c_void_p, c_void_p],
     "kmb_cast_bf16": [c_void_p, c_void_p, c_int64, c_void_p],
     "kmb_repack_img_weight": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],

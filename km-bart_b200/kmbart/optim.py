@@ -63,7 +63,7 @@ class AdamW(torch.optim.Optimizer):
         table = torch.tensor(rows, dtype=torch.int64).to(dev)
         cm = torch.tensor(cmap, dtype=torch.int32).to(dev)
         step0 = max((self.state[p]["step"] for p in plist), default=0)
-        step_dev = torch.tensor([step0], dtype=torch.int32, device=dev)
+        step_dev = torch.tensor([step0, 0], dtype=torch.int32, device=dev)   # {step, float step_size}
         sig = tuple(rows)
         return {"sig": sig, "table": table, "cmap": cm, "n_chunks": len(cmap) // 2, "step": step_dev, "plist": plist}
 

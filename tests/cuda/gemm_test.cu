@@ -151,8 +151,10 @@ int main(int argc, char** argv) {
   for (int amn = 0; amn < 2; ++amn) for (int bmn = 0; bmn < 2; ++bmn) {
     fails += run_case(384, 768, 1000, amn, bmn, 0, 0, 1);
     fails += run_case(1000, 264, 328, amn, bmn, 0, 256, 0);
-    fails += run_case(256, 256, 96, amn, bmn, 1, 128, 0);   // tf32
-    fails += run_case(200, 136, 100, amn, bmn, 1, 0, 1);    // tf32 ragged
+    if (!amn && !bmn) {   // tf32 (fp32-parity mode) is K-major only
+      fails += run_case(256, 256, 96, 0, 0, 1, 128, 0);
+      fails += run_case(200, 136, 100, 0, 0, 1, 0, 1);
+    }
   }
   fails += run_case(256, 512, 8192, 1, 1, 0, 0, 2);    // split-K reds
   fails += run_case(768, 768, 12800, 1, 1, 0, 0, 2);
