@@ -9,7 +9,7 @@ LIB := $(PKG)/libkmbart_sm100.so
 
 all: $(LIB) tests
 
-build/%.o: $(PKG)/csrc/%.cu $(PKG)/csrc/common.cuh include/kmbart.h
+build/%.o: $(PKG)/csrc/%.cu $(wildcard $(PKG)/csrc/*.cuh) include/kmbart.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

@@ -94,12 +94,18 @@ typedef struct KmbGemmEpilogue {
   const float* ce_gscale;/* device scalar: upstream_grad / n_valid */
 } KmbGemmEpilogue;
 
+/* tile_n: 0 = choose from (M, N) with the ingest/wave cost model; 32/64/128/256 = single-CTA 128 x tile_n
+ * tiles (tcgen05 cta_group::1); 1128/1192/1256 = CTA-pair 256 x (tile_n - 1000) tiles (cta_group::2,
+ * bf16 only; 192 needs a K-major B). */
 int kmb_gemm(const void* A, const void* B, int M, int N, int K, int64_t lda, int64_t ldb,
              int a_mn, int b_mn, int elt, const KmbGemmEpilogue* epi, int tile_n,
              kmb_stream_t stream);
 /* number of n-tiles kmb_gemm will use for (N, tile_n) — sizes ce_max / ce_sum */
 int kmb_gemm_n_tiles(int N, int tile_n);
 int kmb_gemm_pick_tile_n(int M, int N);
+/* debug aid: enable the block-0 in-kernel timeline (globaltimer ns at entry / setup done / first operands landed /
+ * first accumulator complete / first epilogue done / last epilogue done / exit) and read it back */
+int kmb_gemm_debug_timeline(int enable, int pair, unsigned long long* out7);
 
 /* ------------------------------------------------------------------------------
  * Fused multi-head attention, head_dim = 64, bf16 in/out, fp32 online softmax.

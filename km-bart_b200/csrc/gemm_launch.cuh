@@ -1,0 +1,62 @@
+// Host-side launch helper shared by the two translation units that instantiate gemm_tc05_kernel
+// (single-CTA tiles in gemm_tc05.cu, CTA-pair tiles in gemm_pair.cu; split so they compile in parallel).
+#pragma once
+#include "gemm_kernel.cuh"
+
+namespace kmb {
+
+inline int gemm_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int ELT, int A_MN, int B_MN, int CG>
+static int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmPre,
+                       const GemmParams& p, cudaStream_t st) {
+  using C = Cfg<BN, CG>;
+  auto kern = gemm_tc05_kernel<BN, ELT, A_MN, B_MN, CG>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      kmb_set_last_error(cudaGetErrorString(e), __FILE__, __LINE__);
+      return KMB_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles * p.split_k;
+  const int groups = gemm_num_sms() / CG;
+  const int grid = (tiles < groups ? tiles : groups) * CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG == 2 ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmPre, p);
+  if (e != cudaSuccess) {
+    kmb_set_last_error(cudaGetErrorString(e), __FILE__, __LINE__);
+    return KMB_ERR_CUDA;
+  }
+  return KMB_OK;
+}
+
+// defined in gemm_pair.cu: CTA-pair (cta_group::2) tiles of 256 x bn, bf16 operands
+int gemm_launch_pair(int bn, int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                     const CUtensorMap& tmPre, const GemmParams& p, cudaStream_t st);
+
+int gemm_pair_read_timeline(unsigned long long* h8);
+
+}  // namespace kmb

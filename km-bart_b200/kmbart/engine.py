@@ -412,7 +412,7 @@ class Engine:
 
     def _lm_loss_fwd(self, plan, a, Md, factor, add_total):
         cfg, st, d, V = self.cfg, self.store, self.cfg.d_model, self.cfg.vocab_size
-        tile_n = 256
+        tile_n = 1256   # CTA-pair 256 x 256 tiles
         nt = self.lib.kmb_gemm_n_tiles(V, tile_n)
         ce_max = self.buf(a, "ce_max", (Md, nt), F32)
         ce_sum = self.buf(a, "ce_sum", (Md, nt), F32)
@@ -524,7 +524,7 @@ class Engine:
         dyb_d = self.buf(a, "g.dyb_d", (Md, d), BF16)
         E16 = st.p16(self.n("shared.weight"))
         bwd.add(self.lib.kmb_ce_gscale, _ptr(a["ce_acc"]), _ptr(self.upstream), float(a["lm_factor"]), _ptr(gscale), bwd.stream)
-        self.gemm(bwd, a["dec_b16"], E16, Md, V, d, d, d, tile_n=256, mode=L.EPI_CE_GRAD, bias=a["flb"], labels=a["labels"],
+        self.gemm(bwd, a["dec_b16"], E16, Md, V, d, d, d, tile_n=1256, mode=L.EPI_CE_GRAD, bias=a["flb"], labels=a["labels"],
                   ce_lse=a["ce_lse"], ce_gscale=gscale, out_bf16=dlog, ld_bf16=V)
         self.gemm(bwd, dlog, E16, Md, d, V, V, d, b_mn=1, out_bf16=dyb_d)
         self.gemm(bwd, dlog, a["dec_b16"], V, d, Md, V, d, a_mn=1, b_mn=1, out_f32=st.g(self.n("shared.weight")), ld_f32=d, accumulate=lm_acc)

@@ -37,6 +37,7 @@ _PROTOS = {
                  C.POINTER(GemmEpilogue), c_int, c_void_p],
     "kmb_gemm_n_tiles": [c_int, c_int],
     "kmb_gemm_pick_tile_n": [c_int, c_int],
+    "kmb_gemm_debug_timeline": [c_int, c_int, c_void_p],
     "kmb_attn_fwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                      c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
     "kmb_attn_fwd_strided": [c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_int64), c_void_p,

@@ -139,6 +139,41 @@ int main(int argc, char** argv) {
     bench_case(12800, 3072, 768, 0, 0, 256, "fc1");
     return 0;
   }
+  if (argc > 1 && !strcmp(argv[1], "timeline")) {   // where does a launch spend its time? (block 0, ns)
+    for (int mode = 0; mode < 2; ++mode) {
+      g_noout = mode == 0;
+      for (int tn : {256, 1256}) {
+        int shapes[4][3] = {{18944, 256, 768}, {18944, 2048, 768}, {18944, 256, 3072}, {12800, 2304, 768}};
+        for (auto& sh : shapes) {
+          kmb_gemm_debug_timeline(1, 0, nullptr);
+          bench_case(sh[0], sh[1], sh[2], 0, 0, tn, "tl");
+          CK(cudaDeviceSynchronize());
+          unsigned long long t[7];
+          kmb_gemm_debug_timeline(0, tn > 1000, t);
+          printf("   timeline ns: setup %llu  first-load %llu  first-acc %llu  first-epi %llu  last-epi %llu  exit %llu\n", t[1] - t[0],
+                 t[2] - t[0], t[3] - t[0], t[4] - t[0], t[5] - t[0], t[6] - t[0]);
+        }
+      }
+    }
+    return 0;
+  }
+  if (argc > 1 && !strcmp(argv[1], "sweep")) {   // mainloop / epilogue decomposition (profiles/)
+    for (int mode = 0; mode < 3; ++mode) {
+      g_noout = mode == 0; g_gelu = mode == 2;
+      printf("--- mode %s\n", mode == 0 ? "no output (mainloop bound)" : mode == 1 ? "bf16 out" : "gelu + preact + bf16 out");
+      for (int tn : {256, 1256}) {
+        bench_case(8192, 8192, 8192, 0, 0, tn, "big");
+        bench_case(18944, 2048, 8192, 0, 0, tn, "1wave-longK");   // 148 single tiles x 8 = 8 waves exactly / 74 pairs x 8
+        bench_case(18944, 2048, 768, 0, 0, tn, "8wave-K768");
+        bench_case(18944, 256, 768, 0, 0, tn, "1wave-K768");
+        bench_case(18944, 256, 3072, 0, 0, tn, "1wave-K3072");
+        bench_case(12800, 2304, 768, 0, 0, tn, "qkv");
+        bench_case(12800, 3072, 768, 0, 0, tn, "fc1");
+        bench_case(12800, 768, 3072, 0, 0, tn, "fc2");
+      }
+    }
+    return 0;
+  }
   int fails = 0;
   srand(1);
   // smallest possible first: one tile, one k-block, K-major both

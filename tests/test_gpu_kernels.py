@@ -67,6 +67,9 @@ def pad_cols(t, mult=8):
     (1000, 520, 200, 0, 0, 0), (1000, 520, 200, 0, 1, 128), (1000, 264, 328, 1, 0, 256), (384, 768, 1000, 1, 1, 0),
     (300, 72, 200, 0, 0, 64), (4096, 768, 768, 0, 0, 0), (20000, 256, 64, 0, 0, 128), (17, 40, 24, 0, 0, 32),
     (6144, 2304, 768, 0, 0, 0), (128, 50320, 128, 0, 0, 256),
+    # CTA-pair tiles (cta_group::2): 256 x {256, 192, 128}
+    (1000, 520, 200, 0, 0, 1256), (1000, 520, 200, 0, 0, 1192), (1000, 520, 200, 0, 1, 1128), (1000, 264, 328, 1, 0, 1256),
+    (384, 768, 1000, 1, 1, 1256), (12800, 768, 768, 0, 0, 1192), (300, 1000, 72, 0, 1, 1256), (6144, 768, 3072, 0, 1, 0),
 ])
 def test_gemm_bf16_plain(lib, M, N, K, a_mn, b_mn, tile_n):
     a = rnd(M, K, seed=1)
@@ -80,33 +83,34 @@ def test_gemm_bf16_plain(lib, M, N, K, a_mn, b_mn, tile_n):
     assert (out - ref).abs().max().item() <= 1e-3 * math.sqrt(K)
 
 
-def test_gemm_epilogue_bias_gelu_preact_residual(lib):
+@pytest.mark.parametrize("tile_n", [0, 128, 1256, 1192])
+def test_gemm_epilogue_bias_gelu_preact_residual(lib, tile_n):
     M, N, K = 1000, 520, 200
     a, w, bias, res = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.1), rnd(N, dtype=F32, seed=3), rnd(M, N, dtype=F32, seed=4)
     ref_pre = a.float() @ w.float().t() + bias
     # (a) bias + GELU, bf16 out + pre-activation copy through the TMA-store path
     out, pre = torch.zeros(M, N, device="cuda", dtype=BF16), torch.zeros(M, N, device="cuda", dtype=BF16)
-    run_gemm(lib, a, w, M, N, K, bias=bias, act=lib.ACT_GELU, out_bf16=out, out_preact=pre)
+    run_gemm(lib, a, w, M, N, K, tile_n=tile_n, bias=bias, act=lib.ACT_GELU, out_bf16=out, out_preact=pre)
     assert (pre.float() - ref_pre).abs().max().item() <= 2 ** -7 * ref_pre.abs().max().item()      # one bf16 rounding
     ref = torch.nn.functional.gelu(ref_pre)
     assert (out.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item() + 1e-5
     # (b) bias + residual, fp32 out, then accumulate onto it
     o32 = torch.zeros(M, N, device="cuda", dtype=F32)
-    run_gemm(lib, a, w, M, N, K, bias=bias, residual=res, out_f32=o32)
+    run_gemm(lib, a, w, M, N, K, tile_n=tile_n, bias=bias, residual=res, out_f32=o32)
     assert (o32 - (ref_pre + res)).abs().max().item() <= 1e-4
-    run_gemm(lib, a, w, M, N, K, alpha=0.5, out_f32=o32, accumulate=1)
+    run_gemm(lib, a, w, M, N, K, tile_n=tile_n, alpha=0.5, out_f32=o32, accumulate=1)
     assert (o32 - (ref_pre + res + 0.5 * (ref_pre - bias))).abs().max().item() <= 2e-4
     # (c) GELU backward epilogue: dgrad * gelu'(u), u read from a bf16 aux matrix
     u = rnd(M, N, seed=7)
     du = torch.zeros(M, N, device="cuda", dtype=BF16)
-    run_gemm(lib, a, w, M, N, K, act=lib.ACT_GELU_GRAD, aux=u, out_bf16=du)
+    run_gemm(lib, a, w, M, N, K, tile_n=tile_n, act=lib.ACT_GELU_GRAD, aux=u, out_bf16=du)
     uf = u.float().requires_grad_(True)
     torch.nn.functional.gelu(uf).sum().backward()
     ref = (a.float() @ w.float().t()) * uf.grad
     assert (du.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item() + 1e-4
     # (d) tanh / tanh-grad (BartClassificationHead)
     t = torch.zeros(M, N, device="cuda", dtype=BF16)
-    run_gemm(lib, a, w, M, N, K, bias=bias, act=lib.ACT_TANH, out_bf16=t)
+    run_gemm(lib, a, w, M, N, K, tile_n=tile_n, bias=bias, act=lib.ACT_TANH, out_bf16=t)
     assert (t.float() - torch.tanh(ref_pre)).abs().max().item() <= 2 ** -8 + 1e-5
 
 
@@ -161,7 +165,8 @@ def test_gemm_dropout_epilogue_is_deterministic_and_unbiased(lib):
 
 
 # ------------------------------------------------------------------ fused LM head + cross entropy
-def test_lmhead_ce_forward_backward_never_materialises_logits(lib):
+@pytest.mark.parametrize("tile_n", [256, 1256])
+def test_lmhead_ce_forward_backward_never_materialises_logits(lib, tile_n):
     M, V, d = 300, 50320, 128
     h, E = rnd(M, d, seed=1), rnd(V, d, seed=2, scale=0.05)
     flb = rnd(V, dtype=F32, seed=3, scale=0.1)
@@ -169,11 +174,11 @@ def test_lmhead_ce_forward_backward_never_materialises_logits(lib):
     labels = torch.randint(0, V, (M,), device="cuda", generator=g)
     labels[::7] = -100
     L = lib.load()
-    nt = L.kmb_gemm_n_tiles(V, 256)
+    nt = L.kmb_gemm_n_tiles(V, tile_n)
     ce_max, ce_sum = torch.empty(M, nt, device="cuda"), torch.empty(M, nt, device="cuda")
     lab_logit, lse = torch.zeros(M, device="cuda"), torch.empty(M, device="cuda")
     acc2, loss, total = torch.zeros(2, device="cuda"), torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
-    run_gemm(lib, h, E, M, V, d, tile_n=256, mode=lib.EPI_CE_STATS, bias=flb, labels=labels, ce_max=ce_max, ce_sum=ce_sum,
+    run_gemm(lib, h, E, M, V, d, tile_n=tile_n, mode=lib.EPI_CE_STATS, bias=flb, labels=labels, ce_max=ce_max, ce_sum=ce_sum,
              ce_label_logit=lab_logit)
     lib.check(L.kmb_ce_combine(ce_max.data_ptr(), ce_sum.data_ptr(), lab_logit.data_ptr(), labels.data_ptr(), M, nt, lse.data_ptr(),
                                0, acc2.data_ptr(), 1.0, loss.data_ptr(), total.data_ptr(), 0, _stream()), "ce_combine")
@@ -186,7 +191,7 @@ def test_lmhead_ce_forward_backward_never_materialises_logits(lib):
     gscale, up = torch.empty(1, device="cuda"), torch.full((1,), 2.0, device="cuda")
     lib.check(L.kmb_ce_gscale(acc2.data_ptr(), up.data_ptr(), 1.0, gscale.data_ptr(), _stream()), "gscale")
     dlog = torch.zeros(M, V, device="cuda", dtype=BF16)
-    run_gemm(lib, h, E, M, V, d, tile_n=256, mode=lib.EPI_CE_GRAD, bias=flb, labels=labels, ce_lse=lse, ce_gscale=gscale,
+    run_gemm(lib, h, E, M, V, d, tile_n=tile_n, mode=lib.EPI_CE_GRAD, bias=flb, labels=labels, ce_lse=lse, ce_gscale=gscale,
              out_bf16=dlog, ld_bf16=V)
     (2.0 * ref).backward()
     dref = torch.autograd.grad(2.0 * torch.nn.functional.cross_entropy(hf @ E.float().t() + flb, labels, ignore_index=-100), hf)[0]
