@@ -501,7 +501,12 @@ class Engine:
             fwd.add(self.lib.kmb_next_seed, _ptr(self.seed_state), _ptr(self.seed), fwd.stream)
         _, enc_b16 = self._encoder_fwd(fwd, a, B, Se, R, True, p_drop)
         self._decoder_fwd(fwd, a, B, Sd, Se, True, p_drop, enc_b16)
-        self._lm_loss_fwd(fwd, a, Md, a["lm_factor"], add_total=False)
+        if a["has_lm"]:
+            self._lm_loss_fwd(fwd, a, Md, a["lm_factor"], add_total=False)
+        else:
+            fwd.add(_zero, a["loss"])
+        if a["with_heads"]:   # fp32 gradient of the decoder output contributed by the pre-training heads
+            fwd.add(_zero, self.buf(a, "g.dhead", (Md, self.cfg.d_model), F32))
         return fwd
 
     def _build_train_bwd(self, a, acc):
@@ -514,22 +519,28 @@ class Engine:
         acc = int(acc)
         bwd = Plan()
         bwd.stream = a["stream"]
-        if not acc:
-            bwd.add(_zero, st.G[:st.zero_end])
+        has_lm, with_heads = a["has_lm"], a["with_heads"]
+        assert has_lm or with_heads, "backward without any loss term"
+        if not acc:   # (the heads' backward, which runs before this plan, clears the buffer itself: see heads.py)
+            if not with_heads:
+                bwd.add(_zero, st.G[:st.zero_end] if has_lm else st.G)
+            elif not has_lm:
+                bwd.add(_zero, st.G[st.zero_end:])
         lm_acc = acc
         acc = 1   # every other weight gradient accumulates onto the cleared buffer (enables split-K reds)
-        gscale = self.buf(a, "ce_gscale", (1,), F32)
-        dlog = self.buf(a, "dlogits", (Md, V), BF16)
         dpre_d = [self.buf(a, "g.dpreA_d", (Md, d), F32), self.buf(a, "g.dpreB_d", (Md, d), F32)]
         dyb_d = self.buf(a, "g.dyb_d", (Md, d), BF16)
-        E16 = st.p16(self.n("shared.weight"))
-        bwd.add(self.lib.kmb_ce_gscale, _ptr(a["ce_acc"]), _ptr(self.upstream), float(a["lm_factor"]), _ptr(gscale), bwd.stream)
-        self.gemm(bwd, a["dec_b16"], E16, Md, V, d, d, d, tile_n=1256, mode=L.EPI_CE_GRAD, bias=a["flb"], labels=a["labels"],
-                  ce_lse=a["ce_lse"], ce_gscale=gscale, out_bf16=dlog, ld_bf16=V)
-        self.gemm(bwd, dlog, E16, Md, d, V, V, d, b_mn=1, out_bf16=dyb_d)
-        self.gemm(bwd, dlog, a["dec_b16"], V, d, Md, V, d, a_mn=1, b_mn=1, out_f32=st.g(self.n("shared.weight")), ld_f32=d, accumulate=lm_acc)
+        if has_lm:
+            gscale = self.buf(a, "ce_gscale", (1,), F32)
+            dlog = self.buf(a, "dlogits", (Md, V), BF16)
+            E16 = st.p16(self.n("shared.weight"))
+            bwd.add(self.lib.kmb_ce_gscale, _ptr(a["ce_acc"]), _ptr(self.upstream), float(a["lm_factor"]), _ptr(gscale), bwd.stream)
+            self.gemm(bwd, a["dec_b16"], E16, Md, V, d, d, d, tile_n=1256, mode=L.EPI_CE_GRAD, bias=a["flb"], labels=a["labels"],
+                      ce_lse=a["ce_lse"], ce_gscale=gscale, out_bf16=dlog, ld_bf16=V)
+            self.gemm(bwd, dlog, E16, Md, d, V, V, d, b_mn=1, out_bf16=dyb_d)
+            self.gemm(bwd, dlog, a["dec_b16"], V, d, Md, V, d, a_mn=1, b_mn=1, out_f32=st.g(self.n("shared.weight")), ld_f32=d, accumulate=lm_acc)
         # decoder layers, last to first
-        dyA, dyB, flip = None, dyb_d, 0
+        dyA, dyB, flip = (a["g.dhead"] if with_heads else None), (dyb_d if has_lm else None), 0
         denc = self.buf(a, "g.denc", (Me, d), F32)
         Hd, Fd = cfg.decoder_attention_heads, cfg.decoder_ffn_dim
         pad_e = a["pad_e"] if a["has_mask_e"] else None
@@ -603,7 +614,7 @@ class Engine:
         a["row_off"].copy_(a["row_off_host"], non_blocking=True)
 
     def _get_arena(self, mode, input_ids, image_features, attention_mask, decoder_input_ids, labels, training,
-                   lm_factor=1.0, image_counts=None):
+                   lm_factor=1.0, image_counts=None, has_lm=True, with_heads=False):
         B, Se = input_ids.shape
         Sd = decoder_input_ids.shape[1] if decoder_input_ids is not None else 0
         packed = isinstance(image_features, torch.Tensor)
@@ -619,12 +630,14 @@ class Engine:
                         "image_features must be CUDA fp32 [n_i, 2052] tensors"
         R = sum(counts)
         stream = self.stream()
-        key = (mode, B, Se, Sd, R, attention_mask is not None, bool(training), packed, float(lm_factor), stream)
+        key = (mode, B, Se, Sd, R, attention_mask is not None, bool(training), packed, float(lm_factor), stream,
+               bool(has_lm), bool(with_heads))
         a = self.arenas.get(key)
         if a is None:
             dev = self.device
             a = {"__dev": dev, "B": B, "Se": Se, "Sd": Sd, "R": R, "training": bool(training),
-                 "has_mask_e": attention_mask is not None, "stream": stream, "lm_factor": float(lm_factor)}
+                 "has_mask_e": attention_mask is not None, "stream": stream, "lm_factor": float(lm_factor),
+                 "has_lm": bool(has_lm), "with_heads": bool(with_heads)}
             a["ids_e"] = torch.empty(B * Se, dtype=torch.int64, device=dev)
             a["amask_e"] = torch.empty(B * Se, dtype=torch.int64, device=dev)
             a["pad_e"] = torch.zeros(B * Se, dtype=torch.uint8, device=dev)
@@ -649,16 +662,17 @@ class Engine:
 
     # ------------------------------------------------------------------ public: training step pieces
     def train_forward(self, input_ids, image_features, attention_mask, decoder_input_ids, decoder_attention_mask, labels,
-                      final_logits_bias, training, lm_factor=1.0, image_counts=None):
+                      final_logits_bias, training, lm_factor=1.0, image_counts=None, with_heads=False):
         self.sync_shadow()
         a, key = self._get_arena("train", input_ids, image_features, attention_mask, decoder_input_ids, labels, training,
-                                 lm_factor, image_counts)
+                                 lm_factor, image_counts, has_lm=labels is not None, with_heads=with_heads)
         a["flb"] = final_logits_bias.reshape(-1)
         self._stage_inputs(a, input_ids, image_features, attention_mask, decoder_input_ids, decoder_attention_mask, labels)
         plans = self.plans.get(key)
         if plans is None or plans["flb"] != a["flb"].data_ptr():
             plans = {"fwd": self._build_train_fwd(a), "flb": a["flb"].data_ptr()}
             self.plans[key] = plans
+        a["heads_ctx"] = None
         plans["fwd"].run()
         self.last_train = (a, key)
         self.launches_last = len(plans["fwd"])
@@ -676,6 +690,9 @@ class Engine:
         else:
             self.upstream.fill_(1.0)
         plans = self.plans[key]
+        if a.get("heads_ctx"):
+            from .heads import heads_backward
+            heads_backward(self, a, a["heads_ctx"], accumulate)
         name = "bwd1" if accumulate else "bwd0"
         if name not in plans:
             plans[name] = self._build_train_bwd(a, accumulate)

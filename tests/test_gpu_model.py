@@ -277,3 +277,70 @@ def test_base_config_full_size_properties():
     assert changed >= 255     # k_proj biases have ~0 gradient; everything else must move
     l1 = model(**batch)[0].item()
     assert l1 < l0.item()
+
+
+# ------------------------------------------------------------------ multitask pre-training (src/model/model.py:162-309)
+def _pretrain_model(pcfg, psd):
+    from src.model.model import MultiModalBartForPreTraining
+    model = MultiModalBartForPreTraining(product_config(pcfg))
+    load_oracle_weights(model, psd)
+    return model.cuda().train()
+
+
+def _cuda_pretrain_batch(pbatch):
+    out = {}
+    for k, v in pbatch.items():
+        if k == "relation_labels":
+            out[k] = v                      # host dicts, like the reference (src/training.py:45)
+        elif isinstance(v, list):
+            out[k] = [t.cuda() for t in v]
+        else:
+            out[k] = v.cuda()
+    return out
+
+
+def test_pretraining_losses_and_gradients_match_reference_golden(golden):
+    pcfg, psd, pbatch = G.case_pretrain()
+    model = _pretrain_model(pcfg, psd)
+    out = model(**_cuda_pretrain_batch(pbatch))
+    losses = out[0]
+    g = golden["pretrain"]
+    assert set(losses) == set(g["losses"])
+    for k, ref in g["losses"].items():
+        assert abs(losses[k].item() - ref.item()) <= 1e-2 * abs(ref.item()), (k, losses[k].item(), ref.item())
+    lse = torch.logsumexp(out[1].materialize().float().cpu(), -1)
+    assert (lse - g["logits_lse"]).abs().max().item() <= 2e-2
+    losses["loss"].backward()
+    torch.cuda.synchronize()
+    for n, p in model.named_parameters():
+        ref = g["grad_norms"][n].item()
+        assert p.grad is not None, n
+        if ref < 1e-6:
+            assert p.grad.norm().item() <= 1e-4, n
+        else:
+            assert abs(p.grad.norm().item() - ref) <= 3e-2 * ref, (n, p.grad.norm().item(), ref)
+
+
+def test_pretraining_partial_label_sets_and_errors():
+    pcfg, psd, pbatch = G.case_pretrain()
+    model = _pretrain_model(pcfg, psd)
+    cb = _cuda_pretrain_batch(pbatch)
+    with pytest.raises(ValueError):
+        model(**dict(cb, mrm_mask=None))
+    # LM loss only (labels with <cls> positions ignored), then heads only
+    only_lm = {k: v for k, v in cb.items() if k not in ("mrm_labels", "mrm_mask", "attribute_labels", "attribute_mask", "relation_labels")}
+    l1 = model(**only_lm)[0]
+    assert set(l1) == {"lm_loss", "loss"}
+    ref, _ = O.forward_pretraining(psd, pcfg, **{k: v for k, v in pbatch.items() if k in only_lm})
+    assert abs(l1["loss"].item() - ref["loss"].item()) <= 1e-2 * ref["loss"].item()
+    no_lm = {k: v for k, v in cb.items() if k != "labels"}
+    l2 = model(**no_lm)[0]
+    assert "lm_loss" not in l2
+    ref2, _ = O.forward_pretraining(psd, pcfg, **{k: v for k, v in pbatch.items() if k != "labels"})
+    assert abs(l2["loss"].item() - ref2["loss"].item()) <= 1e-2 * ref2["loss"].item()
+    model.zero_grad()
+    l2["loss"].backward()
+    assert model.mrm_head.dense.weight.grad.abs().sum().item() > 0
+    # empty relation list / empty masks are skipped like the reference (no loss entry)
+    empty = dict(cb, relation_labels=[[] for _ in pbatch["relation_labels"]])
+    assert "relation_loss" not in model(**empty)[0]
