@@ -67,14 +67,96 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def make_batch(cfg, seed, device=None, pin=False):
+def make_batch(cfg, seed, device=None, pin=False, batch=B_PER_GPU):
     from oracle import kmbart_oracle as O   # synthetic-batch generator only; not on the timed path
-    b = O.synthetic_batch(cfg, batch=B_PER_GPU, n_regions=R, n_ctx=N_CTX, tgt_len=S_D, seed=seed)
+    b = O.synthetic_batch(cfg, batch=batch, n_regions=R, n_ctx=N_CTX, tgt_len=S_D, seed=seed)
     if pin:
         b = {k: ([t.pin_memory() for t in v] if isinstance(v, list) else v.pin_memory()) for k, v in b.items()}
     if device is not None:
         b = {k: ([t.to(device) for t in v] if isinstance(v, list) else v.to(device)) for k, v in b.items()}
     return b
+
+
+
+GEN_B, GEN_NEW = 64, 24    # BASELINE.json configs[3]: batch 512 over 8 GPUs = 64 samples per GPU, 24 new tokens
+
+
+def bench_generation(model, cfg, dev, rank, world, dist, hbm_peak, peak_src):
+    """KV-cached generation (src/model/mixins.py:33-384 path): tokens/s for greedy, top-k sampling and beam-5 through
+    model.generate(), plus the decode-step kernel chain timed alone (CUDA-graph replays) against the HBM roofline."""
+    from kmbart.decode import get_session
+    model.eval()
+    dev_b = make_batch(cfg, 4321 + rank, device=dev, batch=GEN_B)
+    host_b = make_batch(cfg, 4321 + rank, pin=True, batch=GEN_B)
+    gi = dict(input_ids=dev_b["input_ids"], image_features=dev_b["image_features"], attention_mask=dev_b["attention_mask"])
+    L_ = GEN_NEW + 1
+    modes = {"greedy": dict(max_length=L_, min_length=L_),
+             "sample_top50": dict(max_length=L_, min_length=L_, do_sample=True, top_k=50),
+             "beam5": dict(max_length=L_, min_length=L_ - 1, num_beams=5, early_stopping=True)}
+    out = {"config": f"configs[3] per-GPU share: batch {GEN_B}, S_e=100, {GEN_NEW} new tokens, KV cache, EOS suppressed until the last step",
+           "unit": "tokens/s", "tokens_per_s": {}, "ms_per_call": {}}
+
+    def timed_calls(fn, n):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    with torch.no_grad():
+        for name, kw in modes.items():
+            toks = model.generate(**gi, **kw)      # warm-up: captures the per-step graphs
+            assert toks.shape[0] == GEN_B and toks.shape[1] in (L_ - 1, L_), (name, tuple(toks.shape))   # equal-length beam hypotheses come back without the final EOS
+            ms = timed_calls(lambda: model.generate(**gi, **kw), 3)
+            out["tokens_per_s"][name] = round(GEN_B * world * GEN_NEW / (ms * 1e-3), 1)
+            out["ms_per_call"][name] = round(ms, 3)
+
+        def e2e_call():
+            b = {k: ([t.to(dev, non_blocking=True) for t in v] if isinstance(v, list) else v.to(dev, non_blocking=True))
+                 for k, v in host_b.items() if k in ("input_ids", "image_features", "attention_mask")}
+            return model.generate(**b, **modes["greedy"]).cpu()
+        e2e_call()
+        ms = timed_calls(e2e_call, 3)
+        h2d = sum((sum(t.numel() * t.element_size() for t in v) if isinstance(v, list) else v.numel() * v.element_size())
+                  for k, v in host_b.items() if k in ("input_ids", "image_features", "attention_mask"))
+        out["e2e"] = {"value": round(GEN_B * world * GEN_NEW / (ms * 1e-3), 1), "unit": "tokens/s", "mode": "greedy",
+                      "h2d_bytes_per_call": int(h2d), "d2h_bytes_per_call": GEN_B * L_ * 8, "ms_per_call": round(ms, 3)}
+
+        # decode-step chain alone: 24 graph replays (greedy: rows 64 incl. device-side selection; beam: rows 320, model chain only)
+        eng = model._engine()
+        step = {}
+        for label, rows, sel, use_tbl in (("rows64_greedy", GEN_B, dict(do_sample=False, temperature=1.0, top_k=50, eos=cfg.eos_token_id,
+                                                                     pad=cfg.pad_token_id, min_length=L_), False),
+                                          ("rows320_beam5", GEN_B * 5, None, True)):
+            sess = get_session(eng, GEN_B, R + N_CTX, rows, L_, False)
+            enc = torch.zeros(GEN_B, R + N_CTX, cfg.d_model, device=dev)
+            sess.begin(enc, None, cfg.decoder_start_token_id, use_tbl)
+
+            def run_steps():
+                for t in range(GEN_NEW):
+                    sess.step(t, model.final_logits_bias, sel)
+            run_steps()
+            ms = timed_calls(run_steps, 5)
+            us = ms * 1e3 / GEN_NEW
+            nbytes = sum(sess.step_bytes(t) for t in range(GEN_NEW)) / GEN_NEW
+            step[label] = {"us_per_step": round(us, 1), "algorithmic_bytes_per_step": int(nbytes),
+                           "achieved_GBps": round(nbytes / (us * 1e-6) / 1e9, 1), "frac_of_hbm_peak": round(nbytes / (us * 1e-6) / 1e9 / hbm_peak, 4),
+                           "kernels_per_step": sess.launches_per_step}
+        out["decode_step"] = step
+        out["hbm_peak_GBps"] = hbm_peak
+        out["peak_source"] = peak_src
+    model.train()
+    return out
 
 
 def run_ours(args):
@@ -192,6 +274,7 @@ def run_ours(args):
                 "peak_source": peak_src + " burst (kernel timed alone, L2 flushed between launches)",
                 "step_mfu": None}
 
+    gen = bench_generation(model, cfg, dev, rank, world, dist, hbm, peak_src)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -214,7 +297,7 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / args.steps, 3), "api": "model.forward(**batch) list-of-tensors API + loss.backward() + AdamW.step(), loss.item() each step"},
         "gpu_launches": int(launches_step * args.steps),
-        "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary(), "loss": last.get("loss"),
+        "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary(), "loss": last.get("loss"), "gen": gen,
     }
     print(json.dumps(line))
     if dist is not None:

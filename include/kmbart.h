@@ -125,7 +125,25 @@ int kmb_attn_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64
 int kmb_attn_fwd_strided(const void* q, const void* k, const void* v, void* o, const int64_t* strides12,
                          const uint8_t* key_pad, int B, int H, int Sq, int Sk, int head_dim, int causal,
                          float scale, kmb_stream_t stream);
-/* autograd backward of the above; d_scratch: [B, H, Sq] floats. */
+/* Decode-step attention: one query token per row over a preallocated, never-moved cache.
+ * replaces: the cached branch of HF-3.0.2 SelfAttention.forward (torch.cat growth of prev_key / prev_value) and the
+ *   per-step index_select of every cached tensor in _reorder_cache (src/model/mixins.py:419-434).
+ * K/V of (slot, pos, head) live at k + slot*kv_slot_stride + pos*kv_pos_stride + head*64 (elements).  Row j reads
+ * position p from slot slot_tbl[j*tbl_ld + p] (beam ancestry table) or, when slot_tbl is NULL, from slot j / row_div
+ * (cross-attention K/V stored once per sample, shared by its beams).  key_pad: [n_samples, pad_ld] bytes (1 = pad),
+ * indexed by j / row_div, or NULL.  T <= 256 keys. */
+int kmb_decode_attn(const void* q, int64_t q_row_stride, const void* k, const void* v, int64_t kv_slot_stride,
+                    int64_t kv_pos_stride, const int* slot_tbl, int64_t tbl_ld, int row_div, const uint8_t* key_pad,
+                    int64_t pad_ld, void* o, int64_t o_row_stride, int rows, int H, int T, int head_dim, float scale,
+                    kmb_stream_t stream);
+/* Greedy token selection + finished-sentence bookkeeping of one decode step, on device.
+ * replaces: HF-3.0.2 _generate_no_beam_search loop body reached from src/model/mixins.py:368-382 (EOS ban below
+ *   min_length, argmax, pad for finished rows, append, sent_lengths / unfinished_sents update).
+ * eos_token_id < 0 = no EOS handling.  out_tokens [rows, out_ld] receives the token at column cur_len. */
+int kmb_greedy_select(const float* logits, int64_t ld, int rows, int V, int eos_token_id, int pad_token_id,
+                      int ban_eos, int cur_len, int64_t* unfinished, int64_t* sent_len, int64_t* out_tokens,
+                      int64_t out_ld, int64_t* ids_next, kmb_stream_t stream);
+/* autograd backward of kmb_attn_fwd; d_scratch: [B, H, Sq] floats. */
 int kmb_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
                  const void* o, int64_t ldo, const void* d_o, int64_t lddo, const float* lse,
                  float* d_scratch, const uint8_t* key_pad, void* dq, void* dk, void* dv, int64_t lddq,

@@ -1,0 +1,225 @@
+"""KV-cached decode chain — the hot loop of GenerationMixin.generate (reference
+src/model/mixins.py:336-382 -> HF-3.0.2 _generate_no_beam_search / _generate_beam_search, one
+`self(**model_inputs)` per token with torch.cat-grown caches and a per-step index_select of
+every cached tensor, :419-434).
+
+A DecodeSession owns, for one (batch, source length, rows, max_length) shape:
+  * the cross-attention K/V of every decoder layer, computed ONCE per sample ([B*Se, 2d] bf16) and
+    shared by all beams / return sequences of that sample (the reference replicates the encoder
+    states per beam and re-selects the cross K/V every step);
+  * a preallocated self-attention cache [rows, max_len, 3d] per layer; the fused QKV GEMM of step t
+    stores q|k|v of the new token straight into position t (no copies, no cat);
+  * a beam ancestry table slot_tbl[row, pos]: re-ordering beams permutes 4-byte table entries
+    instead of moving the cache;
+  * one CUDA graph per step t holding the whole chain embed -> 6 x (QKV, attention, out-proj, LN,
+    cross-q, cross-attention, out-proj, LN, fc1+GELU, fc2, LN) -> LM head, plus — for greedy and
+    top-k sampling — the token selection and the finished-sentence bookkeeping, so a step is ONE
+    graph launch with no host synchronisation.
+Per-step algorithmic HBM bytes: decoder + LM-head bf16 weights (176 MB for the base model) + the
+self cache read so far + the cross K/V; `step_bytes()` reports them for bench.py."""
+import gc
+import math
+
+import torch
+
+from . import lib as L
+from .engine import Plan, BF16, F32, _ptr
+
+
+class DecodeSession:
+    def __init__(self, eng, B, Se, rows, max_len, has_pad):
+        cfg, dev, d = eng.cfg, eng.device, eng.cfg.d_model
+        self.eng, self.B, self.Se, self.rows, self.max_len, self.has_pad = eng, B, Se, rows, max_len, has_pad
+        assert rows % B == 0
+        self.row_div = rows // B
+        Ld, F_, V = cfg.decoder_layers, cfg.decoder_ffn_dim, cfg.vocab_size
+        self.enc_b16 = torch.empty(B * Se, d, dtype=BF16, device=dev)
+        self.pad_u8 = torch.zeros(B, Se, dtype=torch.uint8, device=dev)
+        self.kv2 = [torch.empty(B * Se, 2 * d, dtype=BF16, device=dev) for _ in range(Ld)]
+        self.cache = [torch.zeros(rows, max_len, 3 * d, dtype=BF16, device=dev) for _ in range(Ld)]
+        self.slot_tbl = torch.arange(rows, dtype=torch.int32, device=dev).view(rows, 1).repeat(1, max_len).contiguous()
+        self.rows_i32 = torch.arange(rows, dtype=torch.int32, device=dev).view(rows, 1)
+        self.ids = torch.zeros(rows, dtype=torch.int64, device=dev)           # token fed to the next step
+        self.x_f32 = [torch.empty(rows, d, dtype=F32, device=dev) for _ in range(2)]
+        self.x_b16 = [torch.empty(rows, d, dtype=BF16, device=dev) for _ in range(2)]
+        self.y_f32, self.y_b16 = torch.empty(rows, d, dtype=F32, device=dev), torch.empty(rows, d, dtype=BF16, device=dev)
+        self.z_f32, self.z_b16 = torch.empty(rows, d, dtype=F32, device=dev), torch.empty(rows, d, dtype=BF16, device=dev)
+        self.ctx, self.q2, self.lin = (torch.empty(rows, d, dtype=BF16, device=dev) for _ in range(3))
+        self.h = torch.empty(rows, F_, dtype=BF16, device=dev)
+        self.logits = torch.empty(rows, V, dtype=F32, device=dev)
+        self.graphs = {}          # (t, mode) -> torch.cuda.CUDAGraph
+        self.use_tbl = False
+        # greedy / sampling bookkeeping (device resident)
+        self.out = torch.zeros(rows, max_len, dtype=torch.int64, device=dev)
+        self.unfinished = torch.ones(rows, dtype=torch.int64, device=dev)
+        self.sent_len = torch.zeros(rows, dtype=torch.int64, device=dev)
+        self.sel = None
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------ one-time per generate() call
+    def begin(self, enc_hidden, attention_mask, decoder_start_token_id, use_tbl):
+        eng, cfg, d = self.eng, self.eng.cfg, self.eng.cfg.d_model
+        st = eng.store
+        self.enc_b16.copy_(enc_hidden.reshape(self.B * self.Se, d))
+        if self.has_pad:
+            torch.eq(attention_mask.reshape(self.B, self.Se), 0, out=self.pad_u8.view(torch.bool))
+        plan = Plan()
+        plan.stream = eng.stream()
+        for l in range(cfg.decoder_layers):
+            lp = eng.n(f"decoder.layers.{l}")
+            eng.gemm(plan, self.enc_b16, st.p16(lp + ".encoder_attn.k_proj.weight", 2 * d), self.B * self.Se, 2 * d, d, d, d,
+                     bias=st.fused32(lp + ".encoder_attn.k_proj.bias", 2), out_bf16=self.kv2[l])
+        plan.run()
+        self.use_tbl = use_tbl
+        if use_tbl:
+            self.slot_tbl.copy_(self.rows_i32.expand(self.rows, self.max_len))
+        self.ids.fill_(decoder_start_token_id)
+        self.out.zero_()
+        self.out[:, 0] = decoder_start_token_id
+        self.unfinished.fill_(1)
+        self.sent_len.fill_(self.max_len)
+
+    # ------------------------------------------------------------------ the kernel chain of step t
+    def _emit_step(self, plan, t):
+        eng, cfg, lib, d = self.eng, self.eng.cfg, self.eng.lib, self.eng.cfg.d_model
+        st, rows, H, F_ = eng.store, self.rows, cfg.decoder_attention_heads, cfg.decoder_ffn_dim
+        scale = math.sqrt(d) if cfg.scale_embedding else 1.0
+        x_f32, x_b16 = self.x_f32[0], self.x_b16[0]
+        plan.add(lib.kmb_embed_ln_fwd, _ptr(self.ids), 0, _ptr(st.p32(eng.n("shared.weight"))),
+                 _ptr(st.p32(eng.n("decoder.embed_positions.weight"))), 0, 0, 0, 0,
+                 _ptr(st.p32(eng.n("decoder.layernorm_embedding.weight"))), _ptr(st.p32(eng.n("decoder.layernorm_embedding.bias"))),
+                 0, _ptr(x_f32), _ptr(x_b16), 0, 0, rows, 1, d, cfg.extra_pos_embeddings + t, 0, scale, 0.0, 0, 0, plan.stream)
+        ml3 = self.max_len * 3 * d
+        tbl = _ptr(self.slot_tbl) if self.use_tbl else 0
+        pad = _ptr(self.pad_u8) if self.has_pad else 0
+        for l in range(cfg.decoder_layers):
+            lp = eng.n(f"decoder.layers.{l}")
+            cache = self.cache[l]
+            slot_t = cache[:, t, :]                       # [rows, 3d] view, row stride max_len*3d
+            eng.gemm(plan, x_b16, st.p16(lp + ".self_attn.q_proj.weight", 3 * d), rows, 3 * d, d, d, d,
+                     bias=st.fused32(lp + ".self_attn.q_proj.bias", 3), out_bf16=slot_t, ld_bf16=ml3)
+            base = cache.data_ptr()
+            plan.add(lib.kmb_decode_attn, slot_t.data_ptr(), ml3, base + 2 * d, base + 4 * d, ml3, 3 * d, tbl, self.max_len, 1, 0, 0,
+                     _ptr(self.ctx), d, rows, H, t + 1, 64, 0.125, plan.stream)
+            eng.gemm(plan, self.ctx, st.p16(lp + ".self_attn.out_proj.weight"), rows, d, d, d, d,
+                     bias=st.p32(lp + ".self_attn.out_proj.bias"), out_bf16=self.lin)
+            eng.ln_fwd(plan, self.lin, x_f32, lp + ".self_attn_layer_norm", None, self.y_f32, self.y_b16, None, None, rows)
+            eng.gemm(plan, self.y_b16, st.p16(lp + ".encoder_attn.q_proj.weight"), rows, d, d, d, d,
+                     bias=st.p32(lp + ".encoder_attn.q_proj.bias"), out_bf16=self.q2)
+            kv = self.kv2[l]
+            plan.add(lib.kmb_decode_attn, _ptr(self.q2), d, kv.data_ptr(), kv.data_ptr() + 2 * d, self.Se * 2 * d, 2 * d, 0, 0,
+                     self.row_div, pad, self.Se, _ptr(self.ctx), d, rows, H, self.Se, 64, 0.125, plan.stream)
+            eng.gemm(plan, self.ctx, st.p16(lp + ".encoder_attn.out_proj.weight"), rows, d, d, d, d,
+                     bias=st.p32(lp + ".encoder_attn.out_proj.bias"), out_bf16=self.lin)
+            eng.ln_fwd(plan, self.lin, self.y_f32, lp + ".encoder_attn_layer_norm", None, self.z_f32, self.z_b16, None, None, rows)
+            eng.gemm(plan, self.z_b16, st.p16(lp + ".fc1.weight"), rows, F_, d, d, d, bias=st.p32(lp + ".fc1.bias"),
+                     act=L.ACT_GELU, out_bf16=self.h)
+            eng.gemm(plan, self.h, st.p16(lp + ".fc2.weight"), rows, d, F_, F_, F_, bias=st.p32(lp + ".fc2.bias"), out_bf16=self.lin)
+            nxt = (l + 1) % 2
+            eng.ln_fwd(plan, self.lin, self.z_f32, lp + ".final_layer_norm", None, self.x_f32[nxt], self.x_b16[nxt], None, None, rows)
+            x_f32, x_b16 = self.x_f32[nxt], self.x_b16[nxt]
+        V = cfg.vocab_size
+        eng.gemm(plan, x_b16, st.p16(eng.n("shared.weight")), rows, V, d, d, d, bias=self.flb, out_f32=self.logits, ld_f32=V)
+
+    # ------------------------------------------------------------------ selection (device side, captured with the step)
+    def _select_greedy_or_sample(self, t, sel):
+        """HF-3.0.2 _generate_no_beam_search body for cur_len = t + 1 (src/model/mixins.py:368-382 dispatch)."""
+        cur_len = t + 1
+        logits = self.logits
+        if not sel["do_sample"]:   # one fused kernel: EOS ban, argmax, pad for finished rows, append, bookkeeping
+            eos = -1 if sel["eos"] is None else int(sel["eos"])
+            pad_id = 0 if sel["pad"] is None else int(sel["pad"])
+            L.check(self.eng.lib.kmb_greedy_select(logits.data_ptr(), logits.shape[1], self.rows, logits.shape[1], eos, pad_id,
+                                                   int(eos >= 0 and cur_len < sel["min_length"]), cur_len, self.unfinished.data_ptr(),
+                                                   self.sent_len.data_ptr(), self.out.data_ptr(), self.max_len, self.ids.data_ptr(),
+                                                   torch.cuda.current_stream(self.eng.device).cuda_stream), "kmb_greedy_select")
+            return
+        if sel["eos"] is not None and cur_len < sel["min_length"]:
+            logits[:, sel["eos"]] = -float("inf")
+        if sel["do_sample"]:
+            scores = logits / sel["temperature"] if sel["temperature"] != 1.0 else logits
+            k = min(max(sel["top_k"], 1), logits.shape[-1])
+            vals, idx = torch.topk(scores, k, dim=-1)       # top-k filter + softmax == softmax over the k survivors
+            probs = torch.softmax(vals, dim=-1)
+            pick = torch.multinomial(probs, num_samples=1)
+            nxt = idx.gather(-1, pick).squeeze(1)
+        else:
+            nxt = torch.argmax(logits, dim=-1)
+        if sel["eos"] is not None:
+            tok = nxt * self.unfinished + sel["pad"] * (1 - self.unfinished)
+        else:
+            tok = nxt
+        self.out[:, cur_len] = tok
+        self.ids.copy_(tok)
+        if sel["eos"] is not None:
+            is_eos = (tok == sel["eos"]).to(torch.int64)
+            newly = self.unfinished * is_eos
+            self.sent_len.copy_(torch.where(newly.bool(), torch.full_like(self.sent_len, cur_len + 1), self.sent_len))
+            self.unfinished.mul_(1 - is_eos)
+
+    def step(self, t, flb, sel=None):
+        """Replay (or first capture) the graph of step t.  sel = None: model chain only (beam search reads
+        self.logits and drives the bookkeeping itself); else greedy / sampling selection is part of the graph."""
+        key = (t, None if sel is None else tuple(sorted(sel.items())), self.use_tbl)
+        g = self.graphs.get(key)
+        if g is None:
+            self.flb = flb.reshape(-1)
+            plan = Plan()
+            plan.stream = None
+            # warm-up run on a side stream (sets function attributes, lets torch ops pick their workspaces)
+            s = torch.cuda.Stream(device=self.eng.device)
+            s.wait_stream(torch.cuda.current_stream(self.eng.device))
+            snapshot = (self.ids.clone(), self.out.clone(), self.unfinished.clone(), self.sent_len.clone())
+            with torch.cuda.stream(s):
+                plan.stream = s.cuda_stream
+                self._emit_step(plan, t)
+                plan.run()
+                if sel is not None:
+                    self._select_greedy_or_sample(t, sel)
+            torch.cuda.current_stream(self.eng.device).wait_stream(s)
+            self.ids.copy_(snapshot[0]); self.out.copy_(snapshot[1]); self.unfinished.copy_(snapshot[2]); self.sent_len.copy_(snapshot[3])
+            g = torch.cuda.CUDAGraph()
+            # destructors of unrelated objects (e.g. the graphs of a discarded model) must not run inside the capture
+            gc.collect()
+            gc_was_enabled = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g, capture_error_mode="relaxed"):
+                    cap = Plan()
+                    cap.stream = torch.cuda.current_stream(self.eng.device).cuda_stream
+                    self._emit_step(cap, t)
+                    cap.run()
+                    if sel is not None:
+                        self._select_greedy_or_sample(t, sel)
+            finally:
+                if gc_was_enabled:
+                    gc.enable()
+            self.graphs[key] = g
+            self.launches_per_step = len(cap)
+            self._keep = getattr(self, "_keep", []) + [cap]
+        g.replay()
+
+    def reorder(self, beam_idx, t):
+        """Beam step bookkeeping: new row j continues parent beam_idx[j] — permute the ancestry table rows (positions
+        <= t) instead of index_select-ing the cache (src/model/mixins.py:419-434)."""
+        self.slot_tbl.copy_(self.slot_tbl.index_select(0, beam_idx))
+        if t + 1 < self.max_len:
+            self.slot_tbl[:, t + 1:] = self.rows_i32
+
+    def step_bytes(self, t):
+        """Algorithmic HBM bytes of step t: weights once + self cache so far + cross K/V + logits."""
+        cfg, d = self.eng.cfg, self.eng.cfg.d_model
+        F_, V, Ld = cfg.decoder_ffn_dim, cfg.vocab_size, cfg.decoder_layers
+        weights = 2 * (Ld * (6 * d * d + 2 * d * F_) + V * d)
+        self_kv = self.rows * Ld * 2 * (t + 1) * d * 2
+        cross_kv = self.B * Ld * 2 * self.Se * d * 2
+        return weights + self_kv + cross_kv
+
+
+def get_session(eng, B, Se, rows, max_len, has_pad):
+    key = ("dec", B, Se, rows, max_len, has_pad)
+    s = eng.arenas.get(key)
+    if s is None:
+        s = DecodeSession(eng, B, Se, rows, max_len, has_pad)
+        eng.arenas[key] = s
+    return s

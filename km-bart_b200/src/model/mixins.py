@@ -178,6 +178,18 @@ class GenerationMixin:
         encoder = self.get_encoder()
         encoder_outputs: tuple = encoder(input_ids, image_features=image_features, attention_mask=attention_mask)
 
+        # ---- fast path: preallocated caches, one CUDA graph per step, device-side token selection (kmbart/decode.py).
+        # Same token semantics as the legacy loops below; knobs the decode chain does not implement fall through.
+        fast_ok = (use_cache and repetition_penalty == 1.0 and no_repeat_ngram_size == 0 and bad_words_ids is None
+                   and not model_specific_kwargs and max_length <= 256 and input_ids.shape[1] <= 256
+                   and ((num_beams == 1 and (not do_sample or top_p == 1.0)) or (num_beams > 1 and not do_sample))
+                   and getattr(self, "_fast_generate", True))
+        if fast_ok:
+            return self._generate_fast(encoder_outputs[0], attention_mask, batch_size, effective_batch_size, effective_batch_mult,
+                                       num_beams, max_length, min_length, do_sample, early_stopping, temperature, top_k,
+                                       pad_token_id, eos_token_id, length_penalty, num_return_sequences, decoder_start_token_id,
+                                       vocab_size)
+
         if num_return_sequences > 1 or num_beams > 1:
             input_ids_len = input_ids.shape[-1]
             attention_mask = attention_mask.unsqueeze(1).expand(batch_size, effective_batch_mult * num_beams, input_ids_len)
@@ -207,6 +219,45 @@ class GenerationMixin:
                                               num_return_sequences=num_return_sequences, length_penalty=length_penalty,
                                               num_beams=num_beams, vocab_size=vocab_size, **common)
         return self._generate_no_beam_search(input_ids, **common)
+
+
+    # ------------------------------------------------------------------ fast decode (same semantics, device-side loop)
+    def _generate_fast(self, enc_hidden, attention_mask, batch_size, effective_batch_size, effective_batch_mult, num_beams,
+                       max_length, min_length, do_sample, early_stopping, temperature, top_k, pad_token_id, eos_token_id,
+                       length_penalty, num_return_sequences, decoder_start_token_id, vocab_size):
+        from kmbart.decode import get_session
+        eng = self._engine()
+        eng.sync_shadow()
+        B, Se = enc_hidden.shape[0], enc_hidden.shape[1]
+        rows = effective_batch_size * num_beams
+        has_pad = bool((attention_mask == 0).any().item()) if attention_mask is not None else False
+        sess = get_session(eng, B, Se, rows, max_length, has_pad)
+        sess.begin(enc_hidden, attention_mask, decoder_start_token_id, use_tbl=num_beams > 1)
+        flb = self.final_logits_bias
+        if num_beams == 1:
+            sel = dict(do_sample=bool(do_sample), temperature=float(temperature), top_k=int(top_k), eos=eos_token_id,
+                       pad=pad_token_id, min_length=int(min_length))
+            steps = max_length - 1
+            for t in range(steps):
+                sess.step(t, flb, sel)
+                if eos_token_id is not None and (t % 8 == 7) and t + 1 < steps and int(sess.unfinished.max().item()) == 0:
+                    break
+            sent_len = sess.sent_len.clone()
+            width = int(sent_len.max().item())
+            decoded = sess.out[:, :width].clone()
+            if int(sent_len.min().item()) != width:
+                assert pad_token_id is not None, "`Pad_token_id` has to be defined if batches have different lengths"
+                beyond = torch.arange(width, device=decoded.device).unsqueeze(0) >= sent_len.unsqueeze(1)
+                decoded[beyond] = pad_token_id
+            return decoded
+        input_ids = torch.full((rows, 1), decoder_start_token_id, dtype=torch.long, device=enc_hidden.device)
+        return self._generate_beam_search(input_ids, cur_len=1, max_length=max_length, min_length=min_length, do_sample=False,
+                                          early_stopping=early_stopping, temperature=temperature, top_k=top_k, top_p=1.0,
+                                          repetition_penalty=1.0, no_repeat_ngram_size=0, bad_words_ids=None,
+                                          pad_token_id=pad_token_id, eos_token_id=eos_token_id, batch_size=effective_batch_size,
+                                          num_return_sequences=num_return_sequences, length_penalty=length_penalty,
+                                          num_beams=num_beams, vocab_size=vocab_size, encoder_outputs=None, attention_mask=None,
+                                          use_cache=True, model_specific_kwargs={}, sess=sess)
 
     # ------------------------------------------------------------------ loops (HF-3.0.2 generation_utils semantics)
     def _use_cache(self, outputs, use_cache):
@@ -292,7 +343,7 @@ class GenerationMixin:
     def _generate_beam_search(self, input_ids, cur_len, max_length, min_length, do_sample, early_stopping, temperature,
                               top_k, top_p, repetition_penalty, no_repeat_ngram_size, bad_words_ids, pad_token_id,
                               eos_token_id, batch_size, num_return_sequences, length_penalty, num_beams, vocab_size,
-                              encoder_outputs, attention_mask, use_cache, model_specific_kwargs):
+                              encoder_outputs, attention_mask, use_cache, model_specific_kwargs, sess=None):
         generated_hyps = [BeamHypotheses(num_beams, max_length, length_penalty, early_stopping=early_stopping)
                           for _ in range(batch_size)]
         beam_scores = torch.zeros((batch_size, num_beams), dtype=torch.float, device=input_ids.device)
@@ -302,12 +353,16 @@ class GenerationMixin:
         past = (encoder_outputs, None) if encoder_outputs is not None else None
         done = [False for _ in range(batch_size)]
         while cur_len < max_length:
-            model_inputs = self.prepare_inputs_for_generation(input_ids, past=past, attention_mask=attention_mask,
-                                                              use_cache=use_cache, **model_specific_kwargs)
-            outputs = self(**model_inputs)
-            next_token_logits = outputs[0][:, -1, :]
-            if self._use_cache(outputs, use_cache):
-                past = outputs[1]
+            if sess is not None:   # fast decode chain: one graph launch, logits land in sess.logits
+                sess.step(cur_len - 1, self.final_logits_bias)
+                next_token_logits = sess.logits
+            else:
+                model_inputs = self.prepare_inputs_for_generation(input_ids, past=past, attention_mask=attention_mask,
+                                                                  use_cache=use_cache, **model_specific_kwargs)
+                outputs = self(**model_inputs)
+                next_token_logits = outputs[0][:, -1, :]
+                if self._use_cache(outputs, use_cache):
+                    past = outputs[1]
             if self.config.is_encoder_decoder and do_sample is False:
                 next_token_logits = self.adjust_logits_during_generation(next_token_logits, cur_len=cur_len,
                                                                          max_length=max_length)
@@ -367,7 +422,10 @@ class GenerationMixin:
             input_ids = input_ids[beam_idx, :]
             input_ids = torch.cat([input_ids, beam_tokens.unsqueeze(1)], dim=-1)
             cur_len = cur_len + 1
-            if past is not None:
+            if sess is not None:
+                sess.reorder(beam_idx, cur_len - 2)
+                sess.ids.copy_(beam_tokens)
+            elif past is not None:
                 past = self._reorder_cache(past, beam_idx)
 
         for batch_idx in range(batch_size):
