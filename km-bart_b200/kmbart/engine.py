@@ -52,6 +52,19 @@ class Plan:
     def __len__(self):
         return len(self.calls)
 
+    # kernels launched per C-ABI call when it is more than one (bench.py's gpu_launches claim)
+    _MULTI = {"kmb_attn_bwd": 3, "kmb_ce_combine": 3, "kmb_embed_bwd": 2, "kmb_adamw_multi": 2}
+
+    def kernel_count(self):
+        n = 0
+        for fn, _ in self.calls:
+            name = getattr(fn, "__name__", "")
+            if name.startswith("kmb_"):
+                n += self._MULTI.get(name, 1)
+            elif fn is _zero:
+                n += 1
+        return n
+
 
 # --------------------------------------------------------------------------- parameters
 _BIG_SUFFIXES = ("q_proj.weight", "k_proj.weight", "v_proj.weight", "out_proj.weight", "fc1.weight", "fc2.weight",
@@ -193,6 +206,7 @@ class Engine:
         self.upstream = torch.ones(1, dtype=F32, device=dev)
         self.last_train = None
         self.launches_last = 0
+        self.grad_reducer = None   # kmbart.parallel.FlatGradReducer: all-reduce points inside the backward plan
 
     # ------------------------------------------------------------------ helpers
     def n(self, name):
@@ -556,6 +570,8 @@ class Engine:
             self._self_block_bwd(bwd, a, tag, lp, dyA, dyB, Md, B, Sd, Hd, a["pad_d"], True, a[tag + "in_b16"], p_drop, 100 + 3 * l, acc,
                                  dpre_d[flip], dyb_d)
             dyA, dyB, flip = dpre_d[flip], dyb_d, flip ^ 1
+            if self.grad_reducer is not None:   # this layer's weight gradients are final: exchange them while the sweep goes on
+                bwd.add(self.grad_reducer.launch_stage, cfg.decoder_layers - 1 - l)
         # decoder embedding
         demb_d = dpre_d[flip]
         scale = math.sqrt(d) if cfg.scale_embedding else 1.0
@@ -576,6 +592,8 @@ class Engine:
             self._self_block_bwd(bwd, a, tag, lp, dyA, dyB, Me, B, Se, He, pad_e, False, a[tag + "in_b16"], p_drop, 10 + 2 * l, acc,
                                  dpre_e[flip], dyb_e)
             dyA, dyB, flip = dpre_e[flip], dyb_e, flip ^ 1
+            if self.grad_reducer is not None:
+                bwd.add(self.grad_reducer.launch_stage, cfg.decoder_layers + cfg.encoder_layers - 1 - l)
         demb_e = dpre_e[flip]
         dvis = self.buf(a, "g.dvis", (max(R, 1), d), BF16)
         self.ln_bwd(bwd, dyA, dyB, a["e.emb_pre"], a["e.emb_mean"], a["e.emb_rstd"], self.n("encoder.layernorm_embedding"), demb_e, None, None, Me,
@@ -589,6 +607,8 @@ class Engine:
             self.gemm(bwd, dvis, a["feats16"], d, self.fin - 4, R, d, self.fin - 4, a_mn=1, b_mn=1, out_f32=st.g(wname),
                       ld_f32=self.fin, accumulate=acc)
             bwd.add(self.lib.kmb_box_wgrad, _ptr(dvis), _ptr(a["boxes"]), _ptr(st.g(wname)), R, d, self.fin, bwd.stream)
+        if self.grad_reducer is not None:
+            bwd.add(self.grad_reducer.finish)
         return bwd
 
     # ------------------------------------------------------------------ input staging
@@ -675,7 +695,7 @@ class Engine:
         a["heads_ctx"] = None
         plans["fwd"].run()
         self.last_train = (a, key)
-        self.launches_last = len(plans["fwd"])
+        self.launches_last = plans["fwd"].kernel_count()
         return a
 
     def grads_alias_flat_buffer(self):
@@ -697,7 +717,7 @@ class Engine:
         if name not in plans:
             plans[name] = self._build_train_bwd(a, accumulate)
         plans[name].run()
-        self.launches_last += len(plans[name])
+        self.launches_last += plans[name].kernel_count()
 
     # ------------------------------------------------------------------ public: inference forward (no cache)
     def infer_forward(self, input_ids, image_features, attention_mask, decoder_input_ids, decoder_attention_mask,
