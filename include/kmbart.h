@@ -131,11 +131,19 @@ int kmb_attn_fwd_strided(const void* q, const void* k, const void* v, void* o, c
  * K/V of (slot, pos, head) live at k + slot*kv_slot_stride + pos*kv_pos_stride + head*64 (elements).  Row j reads
  * position p from slot slot_tbl[j*tbl_ld + p] (beam ancestry table) or, when slot_tbl is NULL, from slot j / row_div
  * (cross-attention K/V stored once per sample, shared by its beams).  key_pad: [n_samples, pad_ld] bytes (1 = pad),
- * indexed by j / row_div, or NULL.  T <= 256 keys. */
+ * indexed by j / row_div, or NULL.  T <= 1024 keys. */
 int kmb_decode_attn(const void* q, int64_t q_row_stride, const void* k, const void* v, int64_t kv_slot_stride,
                     int64_t kv_pos_stride, const int* slot_tbl, int64_t tbl_ld, int row_div, const uint8_t* key_pad,
                     int64_t pad_ld, void* o, int64_t o_row_stride, int rows, int H, int T, int head_dim, float scale,
                     kmb_stream_t stream);
+/* fp32 parity mode attention (north_star "fp32 mode": logits within 1e-4 relative, greedy decode token-identical):
+ * the decode-attention kernel on fp32 q / k / v / o.  Row r belongs to slot r / row_div; with causal_mod = S_q the
+ * rows of a slot are its S_q query positions and row r sees keys <= r % S_q, which makes this the full-sequence
+ * (self, causal or not, and cross) attention of HF-3.0.2 SelfAttention.forward in fp32.  T <= 1024 keys. */
+int kmb_attn_f32(const float* q, int64_t q_row_stride, const float* k, const float* v, int64_t kv_slot_stride,
+                 int64_t kv_pos_stride, int row_div, const uint8_t* key_pad, int64_t pad_ld, float* o,
+                 int64_t o_row_stride, int rows, int H, int T, int head_dim, int causal_mod, float scale,
+                 kmb_stream_t stream);
 /* Greedy token selection + finished-sentence bookkeeping of one decode step, on device.
  * replaces: HF-3.0.2 _generate_no_beam_search loop body reached from src/model/mixins.py:368-382 (EOS ban below
  *   min_length, argmax, pad for finished rows, append, sent_lengths / unfinished_sents update).

@@ -530,75 +530,98 @@ extern "C" int kmb_attn_bwd(const void* q, const void* k, const void* v, int64_t
 //   once per SAMPLE, not once per beam).  One warp per (row, head); scores live in registers.
 namespace kmb {
 struct DecAttnParams {
-  const bf16* q; int64_t q_rs;                       // q of (row, head) at q + row*q_rs + head*64
-  const bf16* k; const bf16* v; int64_t kv_ss, kv_ps; // K/V of (slot, pos, head) at k + slot*kv_ss + pos*kv_ps + head*64
-  const int* slot_tbl; int64_t tbl_ld;               // [rows, tbl_ld] or null
-  int row_div;                                        // slot = row / row_div when slot_tbl is null
-  const uint8_t* key_pad; int64_t pad_ld;            // [n_slots, pad_ld] (1 = padding) indexed by row / row_div, or null
-  bf16* o; int64_t o_rs;
+  const void* q; int64_t q_rs;                        // q of (row, head) at q + row*q_rs + head*64 (elements)
+  const void* k; const void* v; int64_t kv_ss, kv_ps;  // K/V of (slot, pos, head) at k + slot*kv_ss + pos*kv_ps + head*64
+  const int* slot_tbl; int64_t tbl_ld;                // [rows, tbl_ld] or null
+  int row_div;                                         // slot = row / row_div when slot_tbl is null
+  const uint8_t* key_pad; int64_t pad_ld;             // [n_slots, pad_ld] (1 = padding) indexed by row / row_div, or null
+  void* o; int64_t o_rs;
   int rows, H, T;
+  int causal_mod;                                      // > 0: row is query (row % causal_mod) of its slot and sees keys <= it
   float scale;
 };
 
-// Four lanes share one key: each lane holds 16 of the 64 query dims and reads 32 contiguous bytes of the key, so
-// a quad reads the key's whole 128-byte row (full sectors) and a warp scores 8 keys per pass with 2 shuffles.
+template <typename T> struct Ld16;   // 16 consecutive elements -> 16 floats
+template <> struct Ld16<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&f)[16]) {
+    const uint4* q4 = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint4 u = __ldg(q4 + i);
+      const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f[8 * i + 2 * j] = __uint_as_float(ww[j] << 16);
+        f[8 * i + 2 * j + 1] = __uint_as_float(ww[j] & 0xFFFF0000u);
+      }
+    }
+  }
+  static __device__ __forceinline__ float2 load2(const bf16* p) {
+    const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p));
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
+  }
+  static __device__ __forceinline__ void store2(bf16* p, float a, float b) { *reinterpret_cast<uint32_t*>(p) = pack2(a, b); }
+};
+template <> struct Ld16<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[16]) {
+    const float4* q4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 u = __ldg(q4 + i);
+      f[4 * i] = u.x; f[4 * i + 1] = u.y; f[4 * i + 2] = u.z; f[4 * i + 3] = u.w;
+    }
+  }
+  static __device__ __forceinline__ float2 load2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+  static __device__ __forceinline__ void store2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+};
+
+// Four lanes share one key: each lane holds 16 of the 64 query dims and reads 16 contiguous elements of the key, so
+// a quad reads the key's whole row (full sectors) and a warp scores 8 keys per pass with 2 shuffles.
+// ET = bf16: the decode chain.  ET = float: the fp32 parity mode, where the same kernel also serves full-sequence
+// attention (one "row" per query token, causal_mod = S_q).
+template <typename ET>
 __global__ void __launch_bounds__(128) decode_attn_kernel(const DecAttnParams p) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= p.rows * p.H) return;
   const int row = w / p.H, h = w % p.H;
   const int sub = lane & 3, kq = lane >> 2;   // dims [16*sub, 16*sub+16) of key (8*pass + kq)
+  const ET* qb = reinterpret_cast<const ET*>(p.q);
+  const ET* kb = reinterpret_cast<const ET*>(p.k);
+  const ET* vb = reinterpret_cast<const ET*>(p.v);
   float qf[16];
-  {
-    const uint4* qp = reinterpret_cast<const uint4*>(p.q + (int64_t)row * p.q_rs + h * 64 + sub * 16);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const uint4 u = __ldg(qp + i);
-      const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        qf[8 * i + 2 * j] = __uint_as_float(ww[j] << 16);
-        qf[8 * i + 2 * j + 1] = __uint_as_float(ww[j] & 0xFFFF0000u);
-      }
-    }
-  }
+  Ld16<ET>::load(qb + (int64_t)row * p.q_rs + h * 64 + sub * 16, qf);
   const int bslot = row / p.row_div;
-  __shared__ float s_sc[4][256];   // scores / probabilities of this warp's keys (T <= 256)
-  __shared__ int s_slot[4][256];
+  const int T = p.causal_mod > 0 ? min(p.T, row % p.causal_mod + 1) : p.T;
+  __shared__ float s_sc[4][1024];   // scores / probabilities of this warp's keys (T <= 1024)
+  __shared__ int s_slot[4][1024];
   float* sc = s_sc[threadIdx.x >> 5];
   int* sl = s_slot[threadIdx.x >> 5];
   float mx = -INFINITY;
-  for (int pos0 = 0; pos0 < p.T; pos0 += 8) {
+  for (int pos0 = 0; pos0 < T; pos0 += 8) {
     const int pos = pos0 + kq;
     float acc = 0.f;
-    bool ok = pos < p.T;
+    bool ok = pos < T;
     int slot = bslot;
     if (ok) {
       if (p.slot_tbl) slot = p.slot_tbl[(int64_t)row * p.tbl_ld + pos];
       if (p.key_pad && p.key_pad[(int64_t)bslot * p.pad_ld + pos]) ok = false;
     }
     if (ok) {
-      const uint4* kp = reinterpret_cast<const uint4*>(p.k + (int64_t)slot * p.kv_ss + (int64_t)pos * p.kv_ps + h * 64 + sub * 16);
+      float kf[16];
+      Ld16<ET>::load(kb + (int64_t)slot * p.kv_ss + (int64_t)pos * p.kv_ps + h * 64 + sub * 16, kf);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint4 u = __ldg(kp + c);
-        const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc = fmaf(qf[8 * c + 2 * j], __uint_as_float(ww[j] << 16), acc);
-          acc = fmaf(qf[8 * c + 2 * j + 1], __uint_as_float(ww[j] & 0xFFFF0000u), acc);
-        }
-      }
+      for (int j = 0; j < 16; ++j) acc = fmaf(qf[j], kf[j], acc);
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     const float v = ok ? acc * p.scale : -INFINITY;
-    if (sub == 0 && pos < p.T) { sc[pos] = v; sl[pos] = slot; }
+    if (sub == 0 && pos < T) { sc[pos] = v; sl[pos] = slot; }
     mx = fmaxf(mx, v);
   }
   mx = warp_max(mx);
   __syncwarp();
   float sum = 0.f;
-  for (int pos = lane; pos < p.T; pos += 32) {
+  for (int pos = lane; pos < T; pos += 32) {
     const float v = sc[pos];
     const float e = (v == -INFINITY) ? 0.f : __expf(v - mx);   // a fully masked row gives 0/0 = NaN like the reference
     sc[pos] = e;
@@ -607,37 +630,57 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const DecAttnParams p)
   sum = warp_sum(sum);
   __syncwarp();
   const float inv = 1.f / sum;
-  // output: lane owns dims (2*lane, 2*lane+1); one coalesced 128-byte read of V per key
+  // output: lane owns dims (2*lane, 2*lane+1); one coalesced row read of V per key
   float o0 = 0.f, o1 = 0.f;
 #pragma unroll 4
-  for (int pos = 0; pos < p.T; ++pos) {
+  for (int pos = 0; pos < T; ++pos) {
     const float pr = sc[pos];
     if (pr != 0.f) {   // warp-uniform
-      const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p.v + (int64_t)sl[pos] * p.kv_ss + (int64_t)pos * p.kv_ps + h * 64) + lane);
-      o0 = fmaf(pr, __uint_as_float(u << 16), o0);
-      o1 = fmaf(pr, __uint_as_float(u & 0xFFFF0000u), o1);
+      const float2 u = Ld16<ET>::load2(vb + (int64_t)sl[pos] * p.kv_ss + (int64_t)pos * p.kv_ps + h * 64 + 2 * lane);
+      o0 = fmaf(pr, u.x, o0);
+      o1 = fmaf(pr, u.y, o1);
     }
   }
-  *reinterpret_cast<uint32_t*>(p.o + (int64_t)row * p.o_rs + h * 64 + 2 * lane) = pack2(o0 * inv, o1 * inv);
+  Ld16<ET>::store2(reinterpret_cast<ET*>(p.o) + (int64_t)row * p.o_rs + h * 64 + 2 * lane, o0 * inv, o1 * inv);
 }
 }  // namespace kmb
+
+static int decode_attn_common(int elt, const void* q, int64_t q_row_stride, const void* k, const void* v, int64_t kv_slot_stride,
+                              int64_t kv_pos_stride, const int* slot_tbl, int64_t tbl_ld, int row_div, const uint8_t* key_pad,
+                              int64_t pad_ld, void* o, int64_t o_row_stride, int rows, int H, int T, int head_dim, int causal_mod,
+                              float scale, kmb_stream_t stream) {
+  using namespace kmb;
+  const int al = elt == 0 ? 8 : 4;   // 16-byte vector loads
+  if (!q || !k || !v || !o || rows <= 0 || H <= 0 || T <= 0 || T > 1024 || head_dim != DH || row_div <= 0 || (q_row_stride % al) ||
+      (kv_slot_stride % al) || (kv_pos_stride % al) || (o_row_stride % 2) || causal_mod < 0) {
+    kmb_set_last_error("kmb_decode_attn: bad argument (head_dim 64, T <= 1024, 16-byte aligned strides)", __FILE__, __LINE__);
+    return KMB_ERR_ARG;
+  }
+  DecAttnParams p;
+  p.q = q; p.q_rs = q_row_stride; p.k = k; p.v = v; p.kv_ss = kv_slot_stride;
+  p.kv_ps = kv_pos_stride; p.slot_tbl = slot_tbl; p.tbl_ld = tbl_ld; p.row_div = row_div; p.key_pad = key_pad; p.pad_ld = pad_ld;
+  p.o = o; p.o_rs = o_row_stride; p.rows = rows; p.H = H; p.T = T; p.causal_mod = causal_mod; p.scale = scale;
+  const int64_t warps = (int64_t)rows * H;
+  const unsigned blocks = (unsigned)((warps * 32 + 127) / 128);
+  if (elt == 0) decode_attn_kernel<bf16><<<blocks, 128, 0, (cudaStream_t)stream>>>(p);
+  else decode_attn_kernel<float><<<blocks, 128, 0, (cudaStream_t)stream>>>(p);
+  KMB_CHECK_LAUNCH();
+  return KMB_OK;
+}
 
 extern "C" int kmb_decode_attn(const void* q, int64_t q_row_stride, const void* k, const void* v, int64_t kv_slot_stride,
                                int64_t kv_pos_stride, const int* slot_tbl, int64_t tbl_ld, int row_div, const uint8_t* key_pad,
                                int64_t pad_ld, void* o, int64_t o_row_stride, int rows, int H, int T, int head_dim, float scale,
                                kmb_stream_t stream) {
-  using namespace kmb;
-  if (!q || !k || !v || !o || rows <= 0 || H <= 0 || T <= 0 || T > 256 || head_dim != DH || row_div <= 0 || (q_row_stride % 8) ||
-      (kv_slot_stride % 8) || (kv_pos_stride % 8) || (o_row_stride % 2)) {
-    kmb_set_last_error("kmb_decode_attn: bad argument (head_dim 64, T <= 256, 16-byte aligned strides)", __FILE__, __LINE__);
-    return KMB_ERR_ARG;
-  }
-  DecAttnParams p;
-  p.q = (const bf16*)q; p.q_rs = q_row_stride; p.k = (const bf16*)k; p.v = (const bf16*)v; p.kv_ss = kv_slot_stride;
-  p.kv_ps = kv_pos_stride; p.slot_tbl = slot_tbl; p.tbl_ld = tbl_ld; p.row_div = row_div; p.key_pad = key_pad; p.pad_ld = pad_ld;
-  p.o = (bf16*)o; p.o_rs = o_row_stride; p.rows = rows; p.H = H; p.T = T; p.scale = scale;
-  const int warps = rows * H;
-  decode_attn_kernel<<<(warps * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
-  KMB_CHECK_LAUNCH();
-  return KMB_OK;
+  return decode_attn_common(0, q, q_row_stride, k, v, kv_slot_stride, kv_pos_stride, slot_tbl, tbl_ld, row_div, key_pad, pad_ld, o,
+                            o_row_stride, rows, H, T, head_dim, 0, scale, stream);
+}
+
+// fp32 parity mode: same kernel on fp32 q/k/v/o; causal_mod = S_q turns it into full-sequence causal attention
+extern "C" int kmb_attn_f32(const float* q, int64_t q_row_stride, const float* k, const float* v, int64_t kv_slot_stride,
+                            int64_t kv_pos_stride, int row_div, const uint8_t* key_pad, int64_t pad_ld, float* o,
+                            int64_t o_row_stride, int rows, int H, int T, int head_dim, int causal_mod, float scale,
+                            kmb_stream_t stream) {
+  return decode_attn_common(1, q, q_row_stride, k, v, kv_slot_stride, kv_pos_stride, nullptr, 0, row_div, key_pad, pad_ld, o,
+                            o_row_stride, rows, H, T, head_dim, causal_mod, scale, stream);
 }

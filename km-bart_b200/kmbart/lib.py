@@ -44,6 +44,8 @@ _PROTOS = {
                              c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
     "kmb_decode_attn": [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64,
                         c_void_p, c_int64, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "kmb_attn_f32": [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64,
+                     c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
     "kmb_greedy_select": [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                           c_void_p, c_void_p],
     "kmb_attn_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,

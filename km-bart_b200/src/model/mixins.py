@@ -183,7 +183,7 @@ class GenerationMixin:
         fast_ok = (use_cache and repetition_penalty == 1.0 and no_repeat_ngram_size == 0 and bad_words_ids is None
                    and not model_specific_kwargs and max_length <= 256 and input_ids.shape[1] <= 256
                    and ((num_beams == 1 and (not do_sample or top_p == 1.0)) or (num_beams > 1 and not do_sample))
-                   and getattr(self, "_fast_generate", True))
+                   and getattr(self, "_fast_generate", True) and self.precision != "fp32")
         if fast_ok:
             return self._generate_fast(encoder_outputs[0], attention_mask, batch_size, effective_batch_size, effective_batch_mult,
                                        num_beams, max_length, min_length, do_sample, early_stopping, temperature, top_k,

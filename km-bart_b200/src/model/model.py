@@ -135,6 +135,19 @@ class PretrainedBartModel(nn.Module):
 
     _engine_prefix = "model."
 
+    @property
+    def precision(self):
+        """'bf16' (default: tensor-core fast path) or 'fp32' (3xTF32 parity mode, inference only; kmbart/fp32.py)."""
+        import os
+        return os.environ.get("KMBART_PRECISION") or getattr(self.config, "kmb_precision", "bf16")
+
+    def _fp32(self):
+        eng = self._engine()
+        if getattr(eng, "_fp32_path", None) is None:
+            from kmbart.fp32 import Fp32Path
+            eng._fp32_path = Fp32Path(eng)
+        return eng._fp32_path
+
     def _engine(self):
         from kmbart.engine import Engine
         dev = next(self.parameters()).device
@@ -167,6 +180,9 @@ def _core_forward(owner, input_ids, image_features, attention_mask, decoder_inpu
         raise NotImplementedError("attention maps / per-layer states are never materialised by the fused kernels")
     use_cache = use_cache if use_cache is not None else cfg.use_cache
     eng = owner._engine()
+    if owner.precision == "fp32":
+        return _core_forward_fp32(owner, input_ids, image_features, attention_mask, decoder_input_ids, encoder_outputs,
+                                  decoder_attention_mask, decoder_cached_states, use_cache)
     if not use_cache:
         if decoder_input_ids is None:
             decoder_input_ids = _shift_tokens_right(input_ids, cfg.pad_token_id)
@@ -187,6 +203,28 @@ def _core_forward(owner, input_ids, image_features, attention_mask, decoder_inpu
     T = decoder_input_ids.shape[1]
     h_b16, h_f32, caches = eng.decoder_step(decoder_input_ids[:, -1], T - 1, enc_out, pad_u8, decoder_cached_states)
     return h_f32.unsqueeze(1), h_b16, ((enc_out, enc_pad), caches), enc_out
+
+
+def _core_forward_fp32(owner, input_ids, image_features, attention_mask, decoder_input_ids, encoder_outputs,
+                       decoder_attention_mask, decoder_cached_states, use_cache):
+    """fp32 parity mode of _core_forward: same control flow, kernels from kmbart/fp32.py (hidden states stay fp32)."""
+    cfg = owner.config
+    fp = owner._fp32()
+    if encoder_outputs is None:
+        enc = fp.encoder(input_ids, image_features, attention_mask)
+    else:
+        assert isinstance(encoder_outputs, tuple)
+        enc = encoder_outputs[0]
+    if not use_cache:
+        if decoder_input_ids is None:
+            decoder_input_ids = _shift_tokens_right(input_ids, cfg.pad_token_id)
+        dec = fp.decoder_full(enc, attention_mask, decoder_input_ids, decoder_attention_mask)
+        return dec, dec.reshape(-1, dec.shape[-1]), None, enc
+    enc_pad = attention_mask.eq(0) if attention_mask is not None else None
+    pad_u8 = enc_pad.to(torch.uint8).contiguous() if enc_pad is not None else None
+    T = decoder_input_ids.shape[1]
+    h, caches = fp.decoder_step(decoder_input_ids[:, -1], T - 1, enc, pad_u8, decoder_cached_states)
+    return h.unsqueeze(1), h, ((enc, enc_pad), caches), enc
 
 
 class MultiModalBartModel(FromPretrainedMixin, PretrainedBartModel):
@@ -241,6 +279,8 @@ class _LMBase(FromPretrainedMixin, GenerationMixin, PretrainedBartModel):
         self.model._owner_ref = weakref.ref(self)
 
     def _logits(self, h_b16, B, T):
+        if self.precision == "fp32":
+            return self._fp32().logits(h_b16, self.final_logits_bias).view(B, T, self.config.vocab_size)
         return self._engine().logits_from_hidden(h_b16, self.final_logits_bias).view(B, T, self.config.vocab_size)
 
     def _inference_outputs(self, input_ids, image_features, attention_mask, encoder_outputs, decoder_input_ids,
@@ -286,7 +326,9 @@ class MultiModalBartForConditionalGeneration(_LMBase):
                 output_attentions=None, output_hidden_states=None, **unused):
         if labels is not None:
             use_cache = False
-            if encoder_outputs is None and decoder_cached_states is None:
+            if self.precision == "fp32" and torch.is_grad_enabled() and self.training:
+                raise NotImplementedError("fp32 parity mode is inference-only; train with the default bf16 path")
+            if encoder_outputs is None and decoder_cached_states is None and self.precision != "fp32":
                 loss, lazy, enc, _ = self._fused_loss(input_ids, image_features, attention_mask, decoder_input_ids,
                                                       decoder_attention_mask, labels, 1.0)
                 return (loss, lazy, enc)

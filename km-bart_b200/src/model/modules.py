@@ -155,5 +155,7 @@ class MultiModalBartEncoder(nn.Module):
         owner = self._owner()
         if self.training and torch.is_grad_enabled():
             raise NotImplementedError("stand-alone encoder calls are inference-only; train through model.forward(labels=...)")
+        if owner.precision == "fp32":
+            return owner._fp32().encoder(input_ids, image_features, attention_mask), [], []
         enc, _, _ = owner._engine().infer_forward(input_ids, image_features, attention_mask, None, None, encoder_only=True)
         return enc.clone(), [], []

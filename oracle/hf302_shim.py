@@ -777,7 +777,7 @@ def cached_path(url_or_filename, cache_dir=None, force_download=False, proxies=N
 
 
 def install(reference_root="/root/reference"):
-    """Register the stand-in modules and put the reference checkout on sys.path.  Idempotent."""
+    """Register the stand-in modules.  Idempotent."""
     import transformers
     if "transformers.modeling_bart" not in sys.modules:
         me = sys.modules[__name__]
@@ -814,8 +814,8 @@ def install(reference_root="/root/reference"):
                 transformers.AdamW = AdamW
             except Exception:  # lazy-module attribute guard
                 pass
-    if reference_root and os.path.isdir(reference_root) and reference_root not in sys.path:
-        sys.path.insert(0, reference_root)
+    # sys.path is NOT touched here: import_reference() puts the checkout first only for the duration of its imports,
+    # so the product's same-named `src` package keeps resolving everywhere else (incl. spawned test workers)
     return os.path.isdir(reference_root) if reference_root else False
 
 

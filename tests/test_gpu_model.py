@@ -460,3 +460,52 @@ def test_decode_attention_kernel_with_ancestry_table():
             s_ = s_.masked_fill(pad[b].bool(), float("-inf"))
             ref[r, h * 64:(h + 1) * 64] = (torch.softmax(s_, 0)[:, None] * kvf[b, :, d + h * 64:d + (h + 1) * 64]).sum(0).cpu()
     assert (o.float().cpu() - ref).abs().max().item() <= 2e-2
+
+
+# ------------------------------------------------------------------ fp32 parity mode (north_star: logits 1e-4 relative, greedy token-identical)
+def _fp32_model(ocfg, sd):
+    model = make_model(ocfg, sd)
+    model.config.kmb_precision = "fp32"
+    return model
+
+
+def test_fp32_mode_logits_within_1e4_relative(golden, fwd_setup):
+    ocfg, sd, batch, _ = fwd_setup
+    model = _fp32_model(ocfg, sd)
+    cb = to_cuda_batch(batch)
+    g = golden["forward"]
+    with torch.no_grad():
+        out = model(**cb)                                    # labelled: (loss, logits, enc)
+        nb = {k: v for k, v in cb.items() if k != "labels"}
+        cached = model(**nb)                                 # use_cache default: one cached step on the last token
+    assert abs(out[0].item() - g["loss"].item()) <= 1e-5 * g["loss"].item()
+    logits = out[1].float().cpu()
+    ref = g["logits_cols"]
+    assert ((logits[..., G.LOGIT_COLS] - ref).abs().max() / ref.abs().max()).item() <= 1e-4      # tolerance from BASELINE.json north_star
+    assert (torch.logsumexp(logits, -1) - g["logits_lse"]).abs().max().item() <= 1e-4
+    assert torch.equal(logits.argmax(-1), g["logits_argmax"])
+    assert ((out[2].float().cpu() - g["enc"]).abs().max() / g["enc"].abs().max()).item() <= 1e-4
+    refc = g["cached_default_logits_cols"]
+    assert ((cached[0].float().cpu()[..., G.LOGIT_COLS] - refc).abs().max() / refc.abs().max()).item() <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["greedy", "greedy_min_len", "beam3_early", "beam4_ret2", "beam2_lenpen"])
+def test_fp32_mode_decodes_match_reference_token_for_token(golden, fwd_setup, name):
+    ocfg, sd, batch, _ = fwd_setup
+    model = _fp32_model(ocfg, sd)
+    cb = to_cuda_batch(batch)
+    toks = model.generate(input_ids=cb["input_ids"], image_features=cb["image_features"], attention_mask=cb["attention_mask"],
+                          **G.GENERATE_CASES[name])
+    assert torch.equal(toks.cpu(), golden["generate"][name]), name
+
+
+def test_fp32_mode_no_cache_decode_and_training_guard(golden, fwd_setup):
+    ocfg, sd, batch, _ = fwd_setup
+    model = _fp32_model(ocfg, sd)
+    cb = to_cuda_batch(batch)
+    toks = model.generate(input_ids=cb["input_ids"], image_features=cb["image_features"], attention_mask=cb["attention_mask"],
+                          use_cache=False, **G.GENERATE_CASES["greedy"])
+    assert torch.equal(toks.cpu(), golden["generate"]["greedy"])     # SURVEY §4 invariant 3: cache == no cache
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model(**cb)
