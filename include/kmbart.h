@@ -151,6 +151,45 @@ int kmb_attn_f32(const float* q, int64_t q_row_stride, const float* k, const flo
 int kmb_greedy_select(const float* logits, int64_t ld, int rows, int V, int eos_token_id, int pad_token_id,
                       int ban_eos, int cur_len, int64_t* unfinished, int64_t* sent_len, int64_t* out_tokens,
                       int64_t out_ld, int64_t* ids_next, kmb_stream_t stream);
+/* ------------------------------------------------------------------------------
+ * Persistent decode step: the whole cached decoder forward of ONE generation step in one cooperative launch
+ * (embedding + LayerNorm, L decoder layers with self / cross attention over the preallocated caches, FFN), grid-wide
+ * barriers between the dependent sub-steps and a shared-memory weight ring that prefetches each CTA's weight slices
+ * ahead of the barriers.
+ * replaces: one `self(**model_inputs)` iteration of HF-3.0.2 _generate_no_beam_search / _generate_beam_search reached
+ *   from src/model/mixins.py:336-382 — BartDecoder.forward(use_cache=True) with DecoderLayer / SelfAttention cached
+ *   branches (instantiated src/model/model.py:35), i.e. the 67 kernels of the launch-chain version of the same step.
+ * Buffers: x_f32/x_b16 [rows, d] receive the final decoder state (LM-head operand); ctx, q2 [rows, d] bf16, lin
+ * [rows, d] fp32 (MUST be zero on entry the first time; the kernel leaves it consumed-and-cleared as it needs),
+ * h [rows, F] bf16 are scratch; barrier points at ONE 64-bit counter zeroed once per session and used by every launch
+ * of that session.  Layer caches are [rows, max_len, 3d] (q|k|v per position); row j reads position p of the self
+ * cache from row slot_tbl[j * max_len + p] (beam ancestry, or NULL = own row); cross K/V are [n_samples * Se, 2d],
+ * sample = row / row_div; key_pad [n_samples, Se] bytes (1 = pad) or NULL.  d = 768, head_dim 64, max_len and Se <= 512.
+ */
+#define KMB_DECODE_MAX_LAYERS 12
+typedef struct KmbDecodeLayer {
+  const void *w_qkv, *w_o, *w_cq, *w_co, *w_fc1, *w_fc2;      /* bf16 [3d,d] [d,d] [d,d] [d,d] [F,d] [d,F] */
+  const float *b_qkv, *b_o, *b_cq, *b_co, *b_fc1, *b_fc2;
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b; /* self_attn / encoder_attn / final layer norms */
+  void* cache;                                                /* bf16 [rows, max_len, 3d] */
+  const void* cross_kv;                                       /* bf16 [n_samples * Se, 2d] */
+} KmbDecodeLayer;
+typedef struct KmbDecodeStep {
+  int32_t rows, d, H, F, L, t, max_len, Se, row_div, pos_row; /* pos_row = t + position offset (2) */
+  float embed_scale, attn_scale;
+  int32_t nt[6];                                              /* filled by the library */
+  const int64_t* ids;                                         /* [rows] token fed to this step */
+  const float *tok_emb, *pos_emb, *lne_g, *lne_b;             /* fp32 [V,d], [npos,d], layernorm_embedding */
+  const int32_t* slot_tbl;
+  const uint8_t* key_pad;
+  float* x_f32; void* x_b16; void* ctx; float* lin; void* q2; void* h;
+  unsigned long long* barrier;
+  KmbDecodeLayer layers[KMB_DECODE_MAX_LAYERS];
+} KmbDecodeStep;
+int kmb_decode_step(const KmbDecodeStep* step, kmb_stream_t stream);
+/* CTAs of the persistent grid (= SMs of the current device) */
+int kmb_decode_step_grid(void);
+
 /* autograd backward of kmb_attn_fwd; d_scratch: [B, H, Sq] floats. */
 int kmb_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
                  const void* o, int64_t ldo, const void* d_o, int64_t lddo, const float* lse,

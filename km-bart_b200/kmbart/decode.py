@@ -17,8 +17,10 @@ A DecodeSession owns, for one (batch, source length, rows, max_length) shape:
     graph launch with no host synchronisation.
 Per-step algorithmic HBM bytes: decoder + LM-head bf16 weights (176 MB for the base model) + the
 self cache read so far + the cross K/V; `step_bytes()` reports them for bench.py."""
+import ctypes
 import gc
 import math
+import os
 
 import torch
 
@@ -48,6 +50,12 @@ class DecodeSession:
         self.h = torch.empty(rows, F_, dtype=BF16, device=dev)
         self.logits = torch.empty(rows, V, dtype=F32, device=dev)
         self.graphs = {}          # (t, mode) -> torch.cuda.CUDAGraph
+        # persistent single-launch step (csrc/decode_mega.cu); KMBART_DECODE_CHAIN=1 keeps the per-op launch chain
+        self.mega = (d in (128, 768, 1024) and cfg.decoder_attention_heads * 64 == d and F_ % d == 0 and max_len <= 512 and Se <= 512
+                     and Ld <= L.DECODE_MAX_LAYERS and os.environ.get("KMBART_DECODE_CHAIN", "0") != "1")
+        if self.mega:
+            self.lin_f32 = torch.zeros(rows, d, dtype=F32, device=dev)
+            self.grid_barrier = torch.zeros(2, dtype=torch.int64, device=dev)
         self.use_tbl = False
         # greedy / sampling bookkeeping (device resident)
         self.out = torch.zeros(rows, max_len, dtype=torch.int64, device=dev)
@@ -80,9 +88,47 @@ class DecodeSession:
         self.sent_len.fill_(self.max_len)
 
     # ------------------------------------------------------------------ the kernel chain of step t
+    def _mega_args(self, t):
+        """struct KmbDecodeStep of step t (include/kmbart.h)."""
+        eng, cfg, d = self.eng, self.eng.cfg, self.eng.cfg.d_model
+        st = eng.store
+        a = L.DecodeStep()
+        a.rows, a.d, a.H, a.F, a.L, a.t = self.rows, d, cfg.decoder_attention_heads, cfg.decoder_ffn_dim, cfg.decoder_layers, t
+        a.max_len, a.Se, a.row_div, a.pos_row = self.max_len, self.Se, self.row_div, cfg.extra_pos_embeddings + t
+        a.embed_scale = math.sqrt(d) if cfg.scale_embedding else 1.0
+        a.attn_scale = 0.125
+        a.ids = _ptr(self.ids)
+        a.tok_emb = _ptr(st.p32(eng.n("shared.weight")))
+        a.pos_emb = _ptr(st.p32(eng.n("decoder.embed_positions.weight")))
+        a.lne_g = _ptr(st.p32(eng.n("decoder.layernorm_embedding.weight")))
+        a.lne_b = _ptr(st.p32(eng.n("decoder.layernorm_embedding.bias")))
+        a.slot_tbl = _ptr(self.slot_tbl) if self.use_tbl else 0
+        a.key_pad = _ptr(self.pad_u8) if self.has_pad else 0
+        a.x_f32, a.x_b16, a.ctx, a.lin = _ptr(self.x_f32[0]), _ptr(self.x_b16[0]), _ptr(self.ctx), _ptr(self.lin_f32)
+        a.q2, a.h, a.barrier = _ptr(self.q2), _ptr(self.h), _ptr(self.grid_barrier)
+        for l in range(cfg.decoder_layers):
+            lp, y = eng.n(f"decoder.layers.{l}"), a.layers[l]
+            y.w_qkv = _ptr(st.p16(lp + ".self_attn.q_proj.weight", 3 * d))
+            y.b_qkv = _ptr(st.fused32(lp + ".self_attn.q_proj.bias", 3))
+            for key, name in (("o", "self_attn.out_proj"), ("cq", "encoder_attn.q_proj"), ("co", "encoder_attn.out_proj"),
+                              ("fc1", "fc1"), ("fc2", "fc2")):
+                setattr(y, "w_" + key, _ptr(st.p16(f"{lp}.{name}.weight")))
+                setattr(y, "b_" + key, _ptr(st.p32(f"{lp}.{name}.bias")))
+            for i, name in enumerate(("self_attn_layer_norm", "encoder_attn_layer_norm", "final_layer_norm"), 1):
+                setattr(y, f"ln{i}_g", _ptr(st.p32(f"{lp}.{name}.weight")))
+                setattr(y, f"ln{i}_b", _ptr(st.p32(f"{lp}.{name}.bias")))
+            y.cache, y.cross_kv = _ptr(self.cache[l]), _ptr(self.kv2[l])
+        return a
+
     def _emit_step(self, plan, t):
         eng, cfg, lib, d = self.eng, self.eng.cfg, self.eng.lib, self.eng.cfg.d_model
         st, rows, H, F_ = eng.store, self.rows, cfg.decoder_attention_heads, cfg.decoder_ffn_dim
+        V = cfg.vocab_size
+        if self.mega:
+            args = self._mega_args(t)
+            plan.add(lib.kmb_decode_step, ctypes.byref(args), plan.stream, keep=args)
+            eng.gemm(plan, self.x_b16[0], st.p16(eng.n("shared.weight")), rows, V, d, d, d, bias=self.flb, out_f32=self.logits, ld_f32=V)
+            return
         scale = math.sqrt(d) if cfg.scale_embedding else 1.0
         x_f32, x_b16 = self.x_f32[0], self.x_b16[0]
         plan.add(lib.kmb_embed_ln_fwd, _ptr(self.ids), 0, _ptr(st.p32(eng.n("shared.weight"))),
@@ -118,7 +164,6 @@ class DecodeSession:
             nxt = (l + 1) % 2
             eng.ln_fwd(plan, self.lin, self.z_f32, lp + ".final_layer_norm", None, self.x_f32[nxt], self.x_b16[nxt], None, None, rows)
             x_f32, x_b16 = self.x_f32[nxt], self.x_b16[nxt]
-        V = cfg.vocab_size
         eng.gemm(plan, x_b16, st.p16(eng.n("shared.weight")), rows, V, d, d, d, bias=self.flb, out_f32=self.logits, ld_f32=V)
 
     # ------------------------------------------------------------------ selection (device side, captured with the step)

@@ -509,3 +509,83 @@ def test_fp32_mode_no_cache_decode_and_training_guard(golden, fwd_setup):
     model.train()
     with pytest.raises(NotImplementedError):
         model(**cb)
+
+
+# ------------------------------------------------------------------ persistent decode step (csrc/decode_mega.cu)
+def _decode_sessions(model, B, Se, rows, max_len, has_pad):
+    """One DecodeSession per implementation of the step: the single cooperative launch and the per-op launch chain."""
+    from kmbart.decode import DecodeSession
+    eng = model._engine()
+    eng.sync_shadow()
+    out = []
+    for chain in ("0", "1"):
+        os.environ["KMBART_DECODE_CHAIN"] = chain
+        try:
+            out.append(DecodeSession(eng, B, Se, rows, max_len, has_pad))
+        finally:
+            os.environ.pop("KMBART_DECODE_CHAIN", None)
+    assert out[0].mega and not out[1].mega
+    return eng, out
+
+
+@pytest.mark.parametrize("rows_per_sample,has_pad", [(1, False), (5, True)])
+def test_persistent_decode_step_matches_launch_chain_base_size(rows_per_sample, has_pad):
+    """Base model (d = 768, 6 decoder layers), S_e = 100: the logits of steps 0..5 from the one-launch persistent kernel
+    agree with the 68-kernel chain (both bf16 operands / fp32 accumulation; the chain rounds Linear outputs to bf16
+    before the LayerNorm, the persistent kernel keeps them fp32) — including beam ancestry re-ordering and key padding."""
+    import json
+    from src.model.config import MultiModalBartConfig
+    from src.model.model import MultiModalBartForConditionalGeneration
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "configs", "vcg_base.json")) as f:
+        cfg = MultiModalBartConfig.from_dict(json.load(f))
+    torch.manual_seed(0)
+    model = MultiModalBartForConditionalGeneration(cfg).cuda().eval()
+    with torch.no_grad():   # non-trivial biases / LayerNorm parameters
+        g = torch.Generator(device="cuda").manual_seed(3)
+        for n, p in model.named_parameters():
+            if n.endswith(".bias") or "layer_norm" in n or "layernorm" in n:
+                p.add_(0.1 * torch.randn(p.shape, generator=g, device="cuda"))
+    B, Se, max_len = 7, 100, 12
+    rows = B * rows_per_sample
+    eng, (mega, chain) = _decode_sessions(model, B, Se, rows, max_len, has_pad)
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    enc = torch.randn(B, Se, cfg.d_model, generator=gen, device="cuda")
+    mask = torch.ones(B, Se, dtype=torch.long, device="cuda")
+    if has_pad:
+        mask[1, 80:] = 0
+        mask[4, 33:] = 0
+    flb = 0.1 * torch.randn(1, cfg.vocab_size, generator=gen, device="cuda")
+    for s in (mega, chain):
+        s.begin(enc, mask, 0, use_tbl=rows_per_sample > 1)
+    worst = 0.0
+    for t in range(6):
+        ids = torch.randint(3, 50000, (rows,), generator=gen, device="cuda")
+        perm = torch.randint(0, rows_per_sample, (rows,), generator=gen, device="cuda") + \
+            (torch.arange(rows, device="cuda") // rows_per_sample) * rows_per_sample
+        outs = []
+        for s in (mega, chain):
+            s.ids.copy_(ids)
+            s.step(t, flb)
+            outs.append(s.logits.clone())
+            if rows_per_sample > 1:
+                s.reorder(perm, t)
+        assert torch.isfinite(outs[0]).all()
+        worst = max(worst, (outs[0] - outs[1]).abs().max().item())
+        assert (outs[0].argmax(-1) == outs[1].argmax(-1)).float().mean().item() >= 0.9
+    assert worst <= 3e-2, worst
+    assert mega.launches_per_step <= 3 < chain.launches_per_step
+
+
+def test_persistent_decode_step_small_model_vs_oracle(fwd_setup):
+    """Small golden model (d = 128): greedy generation through the persistent step stays within the bf16 near-tie
+    band of the oracle, and the persistent step is the path generate() takes by default."""
+    ocfg, sd, batch, _ = fwd_setup
+    model = make_model(ocfg, sd)
+    cb = to_cuda_batch(batch)
+    gi = dict(input_ids=cb["input_ids"], image_features=cb["image_features"], attention_mask=cb["attention_mask"])
+    toks = model.generate(**gi, max_length=12)
+    eng = model._engine()
+    sessions = [s for k, s in eng.arenas.items() if isinstance(k, tuple) and k and k[0] == "dec"]
+    assert sessions and all(s.mega for s in sessions)
+    assert _near_tie_ok(sd, ocfg, batch, toks, 2e-2)
