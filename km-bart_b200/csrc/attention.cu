@@ -144,6 +144,8 @@ __device__ __forceinline__ void store_rows(bf16* g, int64_t ld, int r_lo, int nr
 
 // ------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t dsm[];
   bf16* sQ = reinterpret_cast<bf16*>(dsm);
   bf16* sK = sQ + TQ * LDS;
@@ -236,6 +238,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 
 // ------------------------------------------------------------------ backward prep: D = rowsum(dO * O)
 __global__ void attn_bwd_prep_kernel(const AttnParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int total = p.B * p.H * p.Sq;
   if (warp >= total) return;
@@ -251,6 +255,8 @@ __global__ void attn_bwd_prep_kernel(const AttnParams p) {
 
 // ------------------------------------------------------------------ backward, query-row owner: dQ
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t dsm[];
   bf16* sQ = reinterpret_cast<bf16*>(dsm);
   bf16* sdO = sQ + TQ * LDS;
@@ -328,6 +334,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
 
 // ------------------------------------------------------------------ backward, key-row owner: dK, dV
 __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t dsm[];
   bf16* sKr = reinterpret_cast<bf16*>(dsm);  // owned key rows: K and V
   bf16* sVr = sKr + TK * LDS;
@@ -463,7 +471,7 @@ extern "C" int kmb_attn_fwd(const void* q, const void* k, const void* v, int64_t
   }
   dim3 grid((Sq + TQ - 1) / TQ, H, B);
   if (set_attn_smem_attrs()) return KMB_ERR_CUDA;
-  attn_fwd_kernel<<<grid, 128, SMEM_FWD, (cudaStream_t)stream>>>(p);
+  launch_pdl(attn_fwd_kernel, dim3(grid), dim3(128), SMEM_FWD, (cudaStream_t)stream, p);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }
@@ -486,7 +494,7 @@ extern "C" int kmb_attn_fwd_strided(const void* q, const void* k, const void* v,
   if (bad) { kmb_set_last_error("kmb_attn_fwd_strided: bad argument", __FILE__, __LINE__); return KMB_ERR_ARG; }
   dim3 grid((Sq + TQ - 1) / TQ, H, B);
   if (set_attn_smem_attrs()) return KMB_ERR_CUDA;
-  attn_fwd_kernel<<<grid, 128, SMEM_FWD, (cudaStream_t)stream>>>(p);
+  launch_pdl(attn_fwd_kernel, dim3(grid), dim3(128), SMEM_FWD, (cudaStream_t)stream, p);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }
@@ -511,12 +519,12 @@ extern "C" int kmb_attn_bwd(const void* q, const void* k, const void* v, int64_t
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int rows = B * H * Sq;
-  attn_bwd_prep_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>(p);
+  launch_pdl(attn_bwd_prep_kernel, dim3((rows * 32 + 255) / 256), dim3(256), 0, st, p);
   KMB_CHECK_LAUNCH();
   if (set_attn_smem_attrs()) return KMB_ERR_CUDA;
-  attn_bwd_dq_kernel<<<dim3((Sq + TQ - 1) / TQ, H, B), 128, SMEM_DQ, st>>>(p);
+  launch_pdl(attn_bwd_dq_kernel, dim3(dim3((Sq + TQ - 1) / TQ, H, B)), dim3(128), SMEM_DQ, st, p);
   KMB_CHECK_LAUNCH();
-  attn_bwd_dkv_kernel<<<dim3((Sk + TK - 1) / TK, H, B), 128, SMEM_DKV, st>>>(p);
+  launch_pdl(attn_bwd_dkv_kernel, dim3(dim3((Sk + TK - 1) / TK, H, B)), dim3(128), SMEM_DKV, st, p);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }

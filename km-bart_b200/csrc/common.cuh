@@ -8,6 +8,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #define KMB_OK 0
 #define KMB_ERR_ARG (-1)
@@ -30,6 +31,30 @@ void kmb_set_last_error(const char* msg, const char* file, int line);
 
 namespace kmb {
 
+// Launch with programmatic stream serialization (KMBART_NO_PDL=1 falls back to plain stream order, for A/B timing).
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("KMBART_NO_PDL");
+    on = (e && e[0] == '1') ? 0 : 1;
+  }
+  return on == 1;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -49,6 +74,13 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every hot kernel starts with pdl_trigger() (the next kernel in the stream may begin launching: its CTAs take the
+// SM resources this grid frees and run their prologue) and executes pdl_wait() before its first global-memory
+// access (returns once the previous grid has completed and its writes are visible).  Host side: launch_pdl().
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -344,6 +344,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const bool tl = p.timeline && blockIdx.x == 0;
@@ -376,6 +377,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // barriers, TMEM and descriptors are set up while the previous kernel drains; no global access before here
   if (tl && threadIdx.x == 0) g_gemm_timeline[1] = gtimer();
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;

@@ -17,6 +17,8 @@ namespace kmb {
 __global__ void __launch_bounds__(256) ce_combine_kernel(const float* pmax, const float* psum, const float* label_logit,
                                                          const int64_t* labels, int M, int n_tiles, float* lse_out,
                                                          float* row_loss, float* acc) {
+  pdl_trigger();
+  pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   float loss = 0.f, cnt = 0.f;
   if (row < M) {
@@ -154,6 +156,8 @@ constexpr int ADAM_CHUNK = 8192;  // elements per block
 
 // chunk_map[i] = (tensor index, chunk index within tensor)
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamTensor* table, const int2* chunk_map, AdamHyper h) {
+  pdl_trigger();
+  pdl_wait();
   const int2 cm = chunk_map[blockIdx.x];
   const AdamTensor t = table[cm.x];
   const int64_t base = (int64_t)cm.y * ADAM_CHUNK;
@@ -247,7 +251,7 @@ extern "C" int kmb_ce_combine(const float* ce_max, const float* ce_sum, const fl
   }
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(acc2, 0, 2 * sizeof(float), st);
-  ce_combine_kernel<<<(M * 32 + 255) / 256, 256, 0, st>>>(ce_max, ce_sum, label_logit, labels, M, n_tiles, lse, row_loss, acc2);
+  launch_pdl(ce_combine_kernel, dim3((M * 32 + 255) / 256), dim3(256), 0, st, ce_max, ce_sum, label_logit, labels, M, n_tiles, lse, row_loss, acc2);
   KMB_CHECK_LAUNCH();
   ce_finalize_kernel<<<1, 1, 0, st>>>(acc2, factor, loss_out, loss_total, add_total);
   KMB_CHECK_LAUNCH();
@@ -293,7 +297,7 @@ extern "C" int kmb_adamw_multi(const void* table_dev, const void* chunk_map_dev,
   h.lr = (float)lr; h.beta1 = (float)beta1; h.beta2 = (float)beta2; h.omb1 = (float)(1.0 - beta1); h.omb2 = (float)(1.0 - beta2);
   h.eps = (float)eps; h.weight_decay = (float)weight_decay; h.lr_wd = (float)(lr * weight_decay);
   h.step = step_dev; h.inv_scale = inv_scale_dev;
-  adamw_multi_kernel<<<n_chunks, 256, 0, st>>>((const AdamTensor*)table_dev, (const int2*)chunk_map_dev, h);
+  launch_pdl(adamw_multi_kernel, dim3(n_chunks), dim3(256), 0, st, (const AdamTensor*)table_dev, (const int2*)chunk_map_dev, h);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }

@@ -45,6 +45,8 @@ __device__ __forceinline__ uint2 pack4(float4 v) {
 // feats bf16 [R, 2048] (tensor-core operand) + boxes fp32 [R, 4] (kept exact: raw pixels)
 __global__ void __launch_bounds__(256) pack_features_kernel(const float* const* ptrs, const int* row_off, int B,
                                                             const float* packed, bf16* feats, float* boxes, int R) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x;
   if (r >= R) return;
   const float* src;
@@ -128,6 +130,8 @@ struct EmbedParams {
 
 template <int NV>
 __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const EmbedParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= p.M) return;
   const int d = p.d;
@@ -230,6 +234,8 @@ struct LnFwdParams {
 
 template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= p.M) return;
   const int d = p.d;
@@ -319,6 +325,8 @@ struct LnBwdParams {
 // Row statistics (mean of g, mean of g*xhat) are block-reduced for LN_RB rows at a time.
 constexpr int LN_RB = 4;
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p, int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   const int d = p.d;
   const int c = threadIdx.x * 4;
   const bool active = c < d;
@@ -414,6 +422,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p, int ro
 __global__ void __launch_bounds__(256) embed_bwd_scatter_kernel(const float* demb, const int64_t* ids, const int* slot_idx,
                                                                 float* d_tok, bf16* dvis, int M, int d, int pad_id,
                                                                 float embed_scale) {
+  pdl_trigger();
+  pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= M) return;
   const int slot = slot_idx ? slot_idx[row] : -1;
@@ -432,6 +442,8 @@ __global__ void __launch_bounds__(256) embed_bwd_scatter_kernel(const float* dem
 
 // dpos[s + off, :] (+)= sum_b demb[b, s, :]
 __global__ void pos_grad_kernel(const float* demb, float* dpos, int B, int S, int d, int pos_offset, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const int s = blockIdx.x;
   for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
     float4 acc = make_float4(0, 0, 0, 0);
@@ -452,6 +464,8 @@ __global__ void pos_grad_kernel(const float* demb, float* dpos, int B, int S, in
 // dWbox[c, j] += sum_r dvis[r, c] * box[r, j]
 __global__ void box_wgrad_kernel(const bf16* dvis, const float* boxes, float* dw_img, int R, int d, int ld_w,
                                  int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d) return;
   const int r0 = blockIdx.y * rows_per_block;
@@ -469,6 +483,8 @@ __global__ void box_wgrad_kernel(const bf16* dvis, const float* boxes, float* dw
 // out[n] += sum_m x[m, n]   (bf16 in, fp32 out) — bias gradients of qkv / fc1 / heads
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* x, int64_t ld, float* out, int M, int N,
                                                           int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
   if (c >= N) return;
   const int r0 = blockIdx.y * rows_per_block;
@@ -524,7 +540,7 @@ extern "C" int kmb_pack_features(const float* const* feat_ptrs, const int* row_o
     return KMB_ERR_ARG;
   }
   if (R == 0) return KMB_OK;
-  pack_features_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(feat_ptrs, row_offsets, B, packed, (bf16*)feats_bf16, boxes, R);
+  launch_pdl(pack_features_kernel, dim3(R), dim3(256), 0, (cudaStream_t)stream, feat_ptrs, row_offsets, B, packed, (bf16*)feats_bf16, boxes, R);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }
@@ -562,7 +578,7 @@ extern "C" int kmb_embed_ln_fwd(const int64_t* ids, const int* slot_idx, const f
   p.pos_index = pos_index; p.embed_scale = embed_scale; p.drop = make_drop(dropout_p, dropout_tag, dropout_seed);
   const int blocks = (M * 32 + 255) / 256;
   cudaStream_t st = (cudaStream_t)stream;
-  KMB_DISPATCH_NV(d, (embed_ln_fwd_kernel<6><<<blocks, 256, 0, st>>>(p)), (embed_ln_fwd_kernel<8><<<blocks, 256, 0, st>>>(p)));
+  KMB_DISPATCH_NV(d, (launch_pdl(embed_ln_fwd_kernel<6>, dim3(blocks), dim3(256), 0, st, p)), (launch_pdl(embed_ln_fwd_kernel<8>, dim3(blocks), dim3(256), 0, st, p)));
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }
@@ -580,7 +596,7 @@ extern "C" int kmb_layernorm_fwd(const void* z_bf16, const float* residual, cons
   p.drop = make_drop(z_bf16 ? dropout_p : 0.f, dropout_tag, dropout_seed);
   const int blocks = (M * 32 + 255) / 256;
   cudaStream_t st = (cudaStream_t)stream;
-  KMB_DISPATCH_NV(d, (ln_fwd_kernel<6><<<blocks, 256, 0, st>>>(p)), (ln_fwd_kernel<8><<<blocks, 256, 0, st>>>(p)));
+  KMB_DISPATCH_NV(d, (launch_pdl(ln_fwd_kernel<6>, dim3(blocks), dim3(256), 0, st, p)), (launch_pdl(ln_fwd_kernel<8>, dim3(blocks), dim3(256), 0, st, p)));
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }
@@ -609,7 +625,7 @@ extern "C" int kmb_layernorm_bwd(const float* dy, const void* dy_bf16, const flo
   if (rows_per_block < 2 * LN_RB) rows_per_block = 2 * LN_RB;
   const int blocks = (M + rows_per_block - 1) / rows_per_block;
   const int threads = ((d / 4) + 31) / 32 * 32;
-  ln_bwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(p, rows_per_block);
+  launch_pdl(ln_bwd_kernel, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, p, rows_per_block);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }
@@ -623,9 +639,9 @@ extern "C" int kmb_embed_bwd(const float* demb, const int64_t* ids, const int* s
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int M = B * S;
-  embed_bwd_scatter_kernel<<<(M * 32 + 255) / 256, 256, 0, st>>>(demb, ids, slot_idx, d_tok, (bf16*)dvis_bf16, M, d, pad_id, embed_scale);
+  launch_pdl(embed_bwd_scatter_kernel, dim3((M * 32 + 255) / 256), dim3(256), 0, st, demb, ids, slot_idx, d_tok, (bf16*)dvis_bf16, M, d, pad_id, embed_scale);
   KMB_CHECK_LAUNCH();
-  pos_grad_kernel<<<S, 192, 0, st>>>(demb, dpos, B, S, d, pos_offset, accumulate_pos);
+  launch_pdl(pos_grad_kernel, dim3(S), dim3(192), 0, st, demb, dpos, B, S, d, pos_offset, accumulate_pos);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }
@@ -637,7 +653,7 @@ extern "C" int kmb_box_wgrad(const void* dvis_bf16, const float* boxes, float* d
     return KMB_ERR_ARG;
   }
   const int rpb = 128;
-  box_wgrad_kernel<<<dim3((d + 127) / 128, (R + rpb - 1) / rpb), 128, 0, (cudaStream_t)stream>>>((const bf16*)dvis_bf16, boxes, dw_img, R, d, ld_w, rpb);
+  launch_pdl(box_wgrad_kernel, dim3(dim3((d + 127) / 128, (R + rpb - 1) / rpb)), dim3(128), 0, (cudaStream_t)stream, (const bf16*)dvis_bf16, boxes, dw_img, R, d, ld_w, rpb);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }
@@ -648,7 +664,7 @@ extern "C" int kmb_colsum_bf16(const void* x, int64_t ld, float* out, int M, int
     return KMB_ERR_ARG;
   }
   const int rpb = 64;
-  colsum_bf16_kernel<<<dim3((N / 2 + 255) / 256, (M + rpb - 1) / rpb), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld, out, M, N, rpb);
+  launch_pdl(colsum_bf16_kernel, dim3(dim3((N / 2 + 255) / 256, (M + rpb - 1) / rpb)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, ld, out, M, N, rpb);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }

@@ -1,0 +1,35 @@
+"""Quick A/B timer: config-2 train step (device-resident batch), CUDA events.  python tests/time_step.py [steps]"""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "km-bart_b200"))
+import torch
+import bench
+from src.model.config import MultiModalBartConfig
+from src.model.model import MultiModalBartForConditionalGeneration
+from kmbart.optim import AdamW
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+cfg = MultiModalBartConfig.from_dict(json.load(open(os.path.join(ROOT, "configs", "vcg_base.json"))))
+torch.manual_seed(0)
+model = MultiModalBartForConditionalGeneration(cfg).cuda().train()
+opt = AdamW(model.parameters(), lr=1e-5)
+batch = bench.make_batch(cfg, 1234, device="cuda")
+
+def step():
+    loss = model(**batch)[0]
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    return loss
+
+for _ in range(5):
+    step()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(steps):
+    loss = step()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / steps
+print(f"train step {ms:.3f} ms  ({128 / ms * 1e3:.0f} samples/s)  loss {loss.item():.5f}  PDL={'off' if os.environ.get('KMBART_NO_PDL') == '1' else 'on'}")
