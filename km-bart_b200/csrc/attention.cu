@@ -423,6 +423,298 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnParams p) {
   store_rows(dvg, p.lddv, r_lo, p.Sk, dv, lane, 1.f, 1.f);
 }
 
+// ------------------------------------------------------------------ backward, fused (Sq, Sk <= 128)
+// One persistent CTA per SM walks the (batch, head) pairs.  Q, dO, K, V of a pair (<= 72 KB) are fetched with
+// cp.async into one of two input buffers while the previous pair is being computed, so HBM latency is hidden
+// without relying on co-resident CTAs.  Per pair:
+//   phase 1  units (16 query rows x 32 keys):  S = QK^T, dP = dO V^T, P = exp(S*scale - lse),
+//            dS = P (dP - D) * scale with D = rowsum(dO o O); P and dS are parked in shared memory as bf16
+//   phase 2  units: key-row owners  dV = P^T dO, dK = dS^T Q  (A operands read transposed with ldmatrix.trans);
+//            query-row owners  dQ = dS K
+// Scores are computed once (the split kernels below recompute them for dQ and again for dK/dV) and no operand is
+// loaded twice.  Same rounding points as the split path: P and dS are rounded to bf16 before the second GEMMs.
+constexpr int FB_THREADS = 512;
+constexpr int FB_WARPS = FB_THREADS / 32;
+constexpr int FB_MAXS = 128;
+constexpr int FB_MAXG = 3;            // (batch, head) pairs processed together when the shapes are small
+constexpr int FB_SMEM_MAX = 232448;   // 227 KB opt-in limit
+
+__host__ __device__ inline int fb_tile_in_bytes(int SqP, int SkP) { return (2 * SqP + 2 * SkP) * LDS * 2; }
+// one input buffer: G x (Q, dO, K, V) | G x 4 key-mask words | G x SqP D | G x SqP lse
+__host__ __device__ inline int fb_buf_bytes(int SqP, int SkP, int G) { return G * (fb_tile_in_bytes(SqP, SkP) + 16 + SqP * 8); }
+__host__ __device__ inline int fb_smem_bytes(int SqP, int SkP, int G) {
+  return 2 * fb_buf_bytes(SqP, SkP, G) + G * 2 * SqP * (SkP + 8) * 2;
+}
+
+__device__ __forceinline__ float dot8_bf16(const uint4& a, const uint4& b) {
+  const uint32_t x[4] = {a.x, a.y, a.z, a.w}, y[4] = {b.x, b.y, b.z, b.w};
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v = fmaf(__uint_as_float(x[i] << 16), __uint_as_float(y[i] << 16), v);
+    v = fmaf(__uint_as_float(x[i] & 0xFFFF0000u), __uint_as_float(y[i] & 0xFFFF0000u), v);
+  }
+  return v;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint4 ldg_nc16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+// out[16 rows x 32 dh-columns (half `hf`)] = A(16 x 16*nks) * Y, A fragments fetched by `afrag(ks, a)`,
+// Y a [k][64] shared-memory tile (row pitch LDS); result stored as bf16 rows r_lo / r_lo + 8 of g
+template <typename AFrag>
+__device__ __forceinline__ void fb_gemm_half(AFrag afrag, int nks, const bf16* y, int hf, bf16* g, int64_t ld, int r_lo,
+                                             int nrows, int lane) {
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  for (int ks = 0; ks < nks; ++ks) {
+    uint32_t a[4];
+    afrag(ks, a);
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t bb[4];
+      ldsm_x4_t(bb, y + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + hf * 32 + np * 16 + (lane >> 4) * 8);
+      mma16816(acc[2 * np], a, bb[0], bb[1]);
+      mma16816(acc[2 * np + 1], a, bb[2], bb[3]);
+    }
+  }
+  const int t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int c = hf * 32 + nt * 8 + 2 * t;
+    if (r_lo < nrows) *reinterpret_cast<uint32_t*>(g + (int64_t)r_lo * ld + c) = pack2(acc[nt][0], acc[nt][1]);
+    if (r_lo + 8 < nrows) *reinterpret_cast<uint32_t*>(g + (int64_t)(r_lo + 8) * ld + c) = pack2(acc[nt][2], acc[nt][3]);
+  }
+}
+
+// D = rowsum(dO o O) and lse of one group, staged through registers: the loads of the NEXT group are issued before
+// phase 2 of the current one and consumed after it, so their latency never sits on the critical path.
+struct FbRowPrefetch {
+  uint4 o[2][2], d[2][2];
+  float l[2];
+};
+
+__global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const AttnParams p, int SqP, int SkP, int G) {
+  pdl_trigger();
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int LDP = SkP + 8;
+  const int tile_in = fb_tile_in_bytes(SqP, SkP);
+  const int buf_bytes = fb_buf_bytes(SqP, SkP, G);
+  bf16* sPall = reinterpret_cast<bf16*>(dsm + 2 * buf_bytes);
+  const int n_tiles = p.B * p.H;
+  const int n_groups = (n_tiles + G - 1) / G;
+  const int nQ = SqP >> 4, nK = SkP >> 4, nKC = (SkP + 31) >> 5;
+  const int nRG = SqP >> 3;   // 8-row groups per tile
+  pdl_wait();
+
+  auto buf_bits = [&](int buf) { return reinterpret_cast<uint32_t*>(dsm + buf * buf_bytes + G * tile_in); };
+  auto buf_D = [&](int buf) { return reinterpret_cast<float*>(dsm + buf * buf_bytes + G * (tile_in + 16)); };
+  auto buf_L = [&](int buf) { return buf_D(buf) + G * SqP; };
+
+  auto issue = [&](int group, int buf) {
+    for (int gi = 0; gi < G; ++gi) {
+      const int tile = group * G + gi;
+      if (tile >= n_tiles) break;
+      const int b = tile / p.H, h = tile % p.H;
+      bf16* sQ = reinterpret_cast<bf16*>(dsm + buf * buf_bytes + gi * tile_in);
+      bf16* sdO = sQ + SqP * LDS;
+      bf16* sK = sdO + SqP * LDS;
+      bf16* sV = sK + SkP * LDS;
+      load_tile_async(sQ, p.q + b * p.sbq + h * p.shq, p.ldq, 0, p.Sq, SqP);
+      load_tile_async(sdO, p.dO + (int64_t)b * p.Sq * p.lddo + h * DH, p.lddo, 0, p.Sq, SqP);
+      load_tile_async(sK, p.k + b * p.sbk + h * p.shk, p.ldk, 0, p.Sk, SkP);
+      load_tile_async(sV, p.v + b * p.sbv + h * p.shv, p.ldv, 0, p.Sk, SkP);
+    }
+    if (warp < 4 * G) {   // key-mask words: bit k of word k/32 set = key k is padding / beyond Sk
+      const int gi = warp >> 2, key = (warp & 3) * 32 + lane;
+      const int tile = group * G + gi;
+      bool masked = true;
+      if (tile < n_tiles) masked = key >= p.Sk || (p.key_pad && p.key_pad[(int64_t)(tile / p.H) * p.Sk + key]);
+      const uint32_t bits = __ballot_sync(0xffffffffu, masked);
+      if (lane == 0) buf_bits(buf)[warp] = bits;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  auto rows_load = [&](int group, FbRowPrefetch& r) {
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {
+      const int rg = warp + ps * FB_WARPS;
+      const int gi = rg / nRG, row = (rg % nRG) * 8 + g;
+      const int tile = group * G + gi;
+      r.o[ps][0] = r.o[ps][1] = r.d[ps][0] = r.d[ps][1] = make_uint4(0, 0, 0, 0);
+      r.l[ps] = -INFINITY;
+      if (rg < G * nRG && tile < n_tiles && row < p.Sq) {
+        const int b = tile / p.H, h = tile % p.H;
+        const bf16* op = p.o + b * p.sbo + h * p.sho + (int64_t)row * p.ldo + t * 16;
+        const bf16* dp = p.dO + ((int64_t)b * p.Sq + row) * p.lddo + h * DH + t * 16;
+        r.o[ps][0] = ldg_nc16(op);
+        r.o[ps][1] = ldg_nc16(op + 8);
+        r.d[ps][0] = ldg_nc16(dp);
+        r.d[ps][1] = ldg_nc16(dp + 8);
+        r.l[ps] = __ldg(p.lse + ((int64_t)b * p.H + h) * p.Sq + row);
+      }
+    }
+  };
+  auto rows_store = [&](const FbRowPrefetch& r, int buf) {
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {
+      const int rg = warp + ps * FB_WARPS;
+      float v = dot8_bf16(r.o[ps][0], r.d[ps][0]) + dot8_bf16(r.o[ps][1], r.d[ps][1]);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (rg < G * nRG && t == 0) {
+        buf_D(buf)[rg * 8 + g] = v;          // rg * 8 + g == gi * SqP + row
+        buf_L(buf)[rg * 8 + g] = r.l[ps];
+      }
+    }
+  };
+
+  const float sl2 = p.scale * 1.4426950408889634f;
+  FbRowPrefetch pre;
+  if ((int)blockIdx.x < n_groups) {
+    issue(blockIdx.x, 0);
+    rows_load(blockIdx.x, pre);
+    rows_store(pre, 0);
+  }
+  int it = 0;
+  for (int group = blockIdx.x; group < n_groups; group += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const bool has_next = group + (int)gridDim.x < n_groups;
+    if (has_next) {
+      issue(group + gridDim.x, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const uint8_t* bbase = dsm + buf * buf_bytes;
+    const uint32_t* sBits = buf_bits(buf);
+    const float* sD = buf_D(buf);
+    const float* sL = buf_L(buf);
+
+    // ---------------- phase 1: P and dS tiles (16 query rows x 32 keys per unit)
+    const int U1 = nQ * nKC;
+    for (int u = warp; u < G * U1; u += FB_WARPS) {
+      const int gi = u / U1, uu = u - gi * U1;
+      if (group * G + gi >= n_tiles) break;
+      const bf16* sQ = reinterpret_cast<const bf16*>(bbase + gi * tile_in);
+      const bf16* sdO = sQ + SqP * LDS;
+      const bf16* sK = sdO + SqP * LDS;
+      const bf16* sV = sK + SkP * LDS;
+      bf16* sP = sPall + gi * 2 * SqP * LDP;
+      bf16* sdS = sP + SqP * LDP;
+      const int qt = uu / nKC, kc = uu - qt * nKC, k0 = kc * 32;
+      const int npmax = min(2, (SkP - k0) >> 4);
+      const int r_lo = qt * 16 + g;
+      float sc[4][4], dp[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f;
+        dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t qf[4], dof[4];
+        const int aoff = (qt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8;
+        ldsm_x4(qf, sQ + aoff);
+        ldsm_x4(dof, sdO + aoff);
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+          if (np < npmax) {
+            const int boff = (k0 + np * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + ks * 16 + ((lane >> 3) & 1) * 8;
+            uint32_t bk[4], bv[4];
+            ldsm_x4(bk, sK + boff);
+            ldsm_x4(bv, sV + boff);
+            mma16816(sc[2 * np], qf, bk[0], bk[1]);
+            mma16816(sc[2 * np + 1], qf, bk[2], bk[3]);
+            mma16816(dp[2 * np], dof, bv[0], bv[1]);
+            mma16816(dp[2 * np + 1], dof, bv[2], bv[3]);
+          }
+        }
+      }
+      // per-row constants: -lse*log2(e), D*scale, and a 32-key mask word (padding | causal | dead row) shifted by 2t
+      const uint32_t kmask = sBits[gi * 4 + kc];
+      float nl[2], dsc[2];
+      uint32_t rm[2];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int row = r_lo + hh * 8;
+        const float l = sL[gi * SqP + row];
+        const bool dead = l == -INFINITY;
+        nl[hh] = dead ? 0.f : -l * 1.4426950408889634f;
+        dsc[hh] = sD[gi * SqP + row] * p.scale;
+        uint32_t m = dead ? 0xFFFFFFFFu : kmask;
+        if (p.causal) {
+          const int sft = row - k0 + 1;   // keys k0 + kl with kl >= sft lie in the future of `row`
+          m |= sft <= 0 ? 0xFFFFFFFFu : (sft >= 32 ? 0u : (0xFFFFFFFFu << sft));
+        }
+        rm[hh] = m >> (2 * t);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        if (nt < 2 * npmax) {
+          float pv[4], dsv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int hh = e >> 1;
+            const bool masked = (rm[hh] >> (nt * 8 + (e & 1))) & 1u;
+            pv[e] = masked ? 0.f : ex2_approx(fmaf(sc[nt][e], sl2, nl[hh]));
+            dsv[e] = pv[e] * fmaf(dp[nt][e], p.scale, -dsc[hh]);
+          }
+          const int off = r_lo * LDP + k0 + nt * 8 + 2 * t;
+          *reinterpret_cast<uint32_t*>(sP + off) = pack2(pv[0], pv[1]);
+          *reinterpret_cast<uint32_t*>(sP + off + 8 * LDP) = pack2(pv[2], pv[3]);
+          *reinterpret_cast<uint32_t*>(sdS + off) = pack2(dsv[0], dsv[1]);
+          *reinterpret_cast<uint32_t*>(sdS + off + 8 * LDP) = pack2(dsv[2], dsv[3]);
+        }
+      }
+    }
+    if (has_next) rows_load(group + gridDim.x, pre);
+    __syncthreads();
+
+    // ---------------- phase 2: units of 16 rows x 32 head-dim columns: dV, dK per key tile, dQ per query tile
+    const int U2 = 2 * (2 * nK + nQ);
+    for (int u = warp; u < G * U2; u += FB_WARPS) {
+      const int gi = u / U2, uu = u - gi * U2;
+      const int tile = group * G + gi;
+      if (tile >= n_tiles) break;
+      const int b = tile / p.H, h = tile % p.H;
+      const bf16* sQ = reinterpret_cast<const bf16*>(bbase + gi * tile_in);
+      const bf16* sdO = sQ + SqP * LDS;
+      const bf16* sK = sdO + SqP * LDS;
+      const bf16* sP = sPall + gi * 2 * SqP * LDP;
+      const bf16* sdS = sP + SqP * LDP;
+      const int hf = uu & 1, v = uu >> 1;
+      if (v < 2 * nK) {
+        const int j0 = (v >> 1) * 16;
+        const bf16* sA = (v & 1) ? sdS : sP;            // dK = dS^T Q ; dV = P^T dO
+        const bf16* sY = (v & 1) ? sQ : sdO;
+        bf16* dst = (v & 1) ? p.dk + (int64_t)b * p.Sk * p.lddk + h * DH : p.dv + (int64_t)b * p.Sk * p.lddv + h * DH;
+        const int64_t ld = (v & 1) ? p.lddk : p.lddv;
+        const bf16* abase = sA + ((lane & 7) + (lane >> 4) * 8) * LDP + j0 + ((lane >> 3) & 1) * 8;
+        fb_gemm_half([&](int ks, uint32_t (&a)[4]) { ldsm_x4_t(a, abase + ks * 16 * LDP); }, nQ, sY, hf, dst, ld, j0 + g, p.Sk, lane);
+      } else {
+        const int qt = v - 2 * nK;
+        const bf16* abase = sdS + (qt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDP + (lane >> 4) * 8;
+        fb_gemm_half([&](int ks, uint32_t (&a)[4]) { ldsm_x4(a, abase + ks * 16); }, nK, sK, hf,
+                     p.dq + (int64_t)b * p.Sq * p.lddq + h * DH, p.lddq, qt * 16 + g, p.Sq, lane);
+      }
+    }
+    if (has_next) rows_store(pre, buf ^ 1);
+    __syncthreads();
+  }
+}
+
 constexpr int SMEM_FWD = (TQ + 2 * SB) * LDS * 2 + SB;
 constexpr int SMEM_DQ = (2 * TQ + 2 * SB) * LDS * 2 + SB;
 constexpr int SMEM_DKV = (2 * TK + 2 * SB) * LDS * 2 + 2 * SB * 4;
@@ -439,6 +731,12 @@ static int set_attn_smem_attrs() {
   }
   done = true;
   return KMB_OK;
+}
+
+// KMBART_ATTN_BWD_SPLIT=1 keeps the three-kernel backward for every shape (A/B timing, tests)
+static bool attn_bwd_fused_enabled() {
+  const char* e = getenv("KMBART_ATTN_BWD_SPLIT");
+  return !(e && e[0] == '1');
 }
 
 static int check_attn_args(const AttnParams& p) {
@@ -518,6 +816,31 @@ extern "C" int kmb_attn_bwd(const void* q, const void* k, const void* v, int64_t
     return KMB_ERR_ARG;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (Sq <= FB_MAXS && Sk <= FB_MAXS && attn_bwd_fused_enabled()) {
+    const int SqP = (Sq + 15) & ~15, SkP = (Sk + 15) & ~15;
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_MAX) != cudaSuccess) {
+        kmb_set_last_error("kmb_attn_bwd: cannot reserve shared memory", __FILE__, __LINE__);
+        return KMB_ERR_CUDA;
+      }
+      attr_set = true;
+    }
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (sms <= 0) sms = 148;
+    }
+    int G = FB_MAXG;   // small shapes: several (batch, head) pairs per iteration keep all 16 warps busy
+    while (G > 1 && (fb_smem_bytes(SqP, SkP, G) > FB_SMEM_MAX || G * SqP > 2 * FB_WARPS * 8)) --G;
+    const int groups = (B * H + G - 1) / G;
+    const int grid = groups < sms ? groups : sms;
+    launch_pdl(attn_bwd_fused_kernel, dim3(grid), dim3(FB_THREADS), (size_t)fb_smem_bytes(SqP, SkP, G), st, p, SqP, SkP, G);
+    KMB_CHECK_LAUNCH();
+    return KMB_OK;
+  }
   const int rows = B * H * Sq;
   launch_pdl(attn_bwd_prep_kernel, dim3((rows * 32 + 255) / 256), dim3(256), 0, st, p);
   KMB_CHECK_LAUNCH();

@@ -53,7 +53,7 @@ class Plan:
         return len(self.calls)
 
     # kernels launched per C-ABI call when it is more than one (bench.py's gpu_launches claim)
-    _MULTI = {"kmb_attn_bwd": 3, "kmb_ce_combine": 3, "kmb_embed_bwd": 2, "kmb_adamw_multi": 2}
+    _MULTI = {"kmb_ce_combine": 3, "kmb_embed_bwd": 2, "kmb_adamw_multi": 2}   # kmb_attn_bwd: 1 fused kernel for S <= 128
 
     def kernel_count(self):
         n = 0

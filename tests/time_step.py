@@ -33,3 +33,20 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 print(f"train step {ms:.3f} ms  ({128 / ms * 1e3:.0f} samples/s)  loss {loss.item():.5f}  PDL={'off' if os.environ.get('KMBART_NO_PDL') == '1' else 'on'}")
+import time
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(steps):
+    step()
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+print(f"host issue time {1e3 * (t1 - t0) / steps:.3f} ms/step")
+# host-side issue cost of ONE step with an empty queue (no back-pressure from the GPU)
+acc = [0.0, 0.0, 0.0]
+for _ in range(5):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); loss = model(**batch)[0]; t1 = time.perf_counter()
+    opt.zero_grad(); loss.backward(); t2 = time.perf_counter()
+    opt.step(); t3 = time.perf_counter()
+    acc[0] += t1 - t0; acc[1] += t2 - t1; acc[2] += t3 - t2
+print("host issue (empty queue) ms: forward %.3f  backward %.3f  optimizer %.3f" % tuple(1e3 * a / 5 for a in acc))
