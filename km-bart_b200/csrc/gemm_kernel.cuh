@@ -317,6 +317,28 @@ __device__ __forceinline__ void stage_bf16_chunk_and_store(float4* st, int& pp, 
   pp ^= 1;
 }
 
+// 32 consecutive bias values (uniform across the warp) as independent 16-byte loads; zeros when
+// bias is null; clamped scalar loads for the ragged last chunk.
+__device__ __forceinline__ void load_bias32(const float* bias, int col0, int N, float (&b)[32]) {
+  if (!bias) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) b[j] = 0.f;
+  } else if (col0 + 32 <= N && (reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t4 = __ldg(b4 + j);
+      b[4 * j] = t4.x; b[4 * j + 1] = t4.y; b[4 * j + 2] = t4.z; b[4 * j + 3] = t4.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int cidx = col0 + j < N ? col0 + j : N - 1;
+      b[j] = __ldg(bias + (cidx < 0 ? 0 : cidx));
+    }
+  }
+}
+
 template <int BN, int ELT, int A_MN, int B_MN, int CG>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -567,34 +589,43 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       } else if (p.e.mode == KMB_EPI_CE_STATS) {
         // online softmax partial over this warp's columns of the tile (+ final_logits_bias);
-        // partial index = n_blk * 2 + half
+        // partial index = n_blk * 2 + half.  The bias slice of a chunk is fetched up front as
+        // independent vector loads (a per-column load -> add -> max chain serialises 32 L2 latencies
+        // per chunk and made this epilogue 4x longer than the tile's MMA time).
         float mx = -INFINITY, sm = 0.f;
         const int64_t label = row_ok ? p.e.labels[row] : -100;
+        constexpr float LOG2E = 1.4426950408889634f;
 #pragma unroll 1
         for (int c = half; c < BN / 32; c += 2) {
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
-          tmem_ld_wait();
           const int col0 = n0 + c * 32;
           int ncols = p.N - col0;
           ncols = ncols > 32 ? 32 : ncols;
+          float v[32];
+          load_bias32(p.e.bias, col0, p.N, v);
+          tmem_ld_wait();
           if (row_ok && ncols > 0) {
-            float v[32];
             float cm = -INFINITY;
+            if (ncols == 32) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[j] = __uint_as_float(r[j]) * p.e.alpha;
-              if (j < ncols) {
-                if (p.e.bias) v[j] += __ldg(p.e.bias + col0 + j);
+              for (int j = 0; j < 32; ++j) {
+                v[j] = fmaf(__uint_as_float(r[j]), p.e.alpha, v[j]);
+                cm = fmaxf(cm, v[j]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                v[j] = j < ncols ? fmaf(__uint_as_float(r[j]), p.e.alpha, v[j]) : -INFINITY;
                 cm = fmaxf(cm, v[j]);
               }
             }
             const float nm = fmaxf(mx, cm);
+            const float nm2 = -nm * LOG2E;
             float cs = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) cs += __expf(v[j] - nm);
-            sm = sm * __expf(mx - nm) + cs;
+            for (int j = 0; j < 32; ++j) cs += fast_ex2(fmaf(v[j], LOG2E, nm2));   // exp(-inf) = 0 past ncols
+            sm = sm * fast_ex2(fmaf(mx, LOG2E, nm2)) + cs;
             mx = nm;
             if (label >= col0 && label < col0 + ncols) {
               float lv = 0.f;
@@ -613,22 +644,23 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int64_t label = row_ok ? p.e.labels[row] : -100;
         const float lse = row_ok ? p.e.ce_lse[row] : 0.f;
         const float gs = (label >= 0) ? *p.e.ce_gscale : 0.f;
+        constexpr float LOG2E = 1.4426950408889634f;
+        const float a2 = p.e.alpha * LOG2E, nl2 = -lse * LOG2E;
 #pragma unroll 1
         for (int c = half; c < BN / 32; c += 2) {
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
-          tmem_ld_wait();
           const int col0 = n0 + c * 32;
+          float v[32];
+          load_bias32(p.e.bias, col0, p.N, v);
+          tmem_ld_wait();
           if (rows_valid > 0 && col0 < p.N) {
-            float v[32];
-            const bool fullc = col0 + 32 <= p.N;
+            const int lj = (int)label - col0;   // column of the label inside this chunk (or out of range)
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(r[j]) * p.e.alpha;
-              if (p.e.bias && (fullc || col0 + j < p.N)) x += __ldg(p.e.bias + col0 + j);
-              float pv = __expf(x - lse);
-              if (col0 + j == (int)label) pv -= 1.f;
-              v[j] = pv * gs;
+              // exp(alpha*acc + bias - lse) in the log2 domain: one FFMA pair + ex2
+              const float pv = fast_ex2(fmaf(__uint_as_float(r[j]), a2, fmaf(v[j], LOG2E, nl2)));
+              v[j] = (pv - (j == lj ? 1.f : 0.f)) * gs;
             }
             stage_bf16_chunk_and_store(st, pp, lane, v, &tmOut, col0, row0);
           }
