@@ -415,6 +415,185 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p, int ro
   }
 }
 
+// ------------------------------------------------------------------ LayerNorm backward, bulk-copy pipelined
+// Same arithmetic as ln_bwd_kernel, restructured for HBM bandwidth: one persistent CTA per SM owns a
+// contiguous row range and streams it through shared memory in LNP_ROWS-row tiles with 1-D bulk copies
+// (cp.async.bulk -> mbarrier complete_tx), LNP stages deep, so 100+ KB per SM are in flight without
+// holding registers.  Per tile: phase A = one warp per row computes the two row statistics from smem;
+// phase B = thread t owns float4 column group t, computes dpre / dz for every row of the tile and keeps
+// the dgamma / dbeta / dbias column sums in 12 registers for the CTA's whole range; they are flushed once
+// with red.global.add.v4.f32 (148 CTAs x d/4 vector reductions instead of ~400 x 3d scalar atomics, whose
+// per-address serialisation in L2 was a ~15 us tail on every launch).
+constexpr int LNP_ROWS = 4;      // rows per tile; 8 / LNP_ROWS warps share a row in phase A
+constexpr int LNP_THREADS = 256;
+constexpr int LNP_WPR = (LNP_THREADS / 32) / LNP_ROWS;
+constexpr int LNP_CTAS_PER_SM = 2;
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float4 lnp_load_dy(const float* sdy, const bf16* sdyb, int idx4, const DropCfg& din, uint32_t key_in,
+                                              uint64_t q) {
+  float4 dy = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (sdy) dy = *reinterpret_cast<const float4*>(sdy + 4 * idx4);
+  if (sdyb) {
+    const uint2 t = *reinterpret_cast<const uint2*>(sdyb + 4 * idx4);
+    dy.x += __uint_as_float(t.x << 16); dy.y += __uint_as_float(t.x & 0xFFFF0000u);
+    dy.z += __uint_as_float(t.y << 16); dy.w += __uint_as_float(t.y & 0xFFFF0000u);
+  }
+  if (din.thresh16) {
+    const uint64_t bits = dropout_bits4_k(key_in, q);
+    dy.x = dropout_keep(bits, 0, din.thresh16) ? dy.x * din.scale : 0.f;
+    dy.y = dropout_keep(bits, 1, din.thresh16) ? dy.y * din.scale : 0.f;
+    dy.z = dropout_keep(bits, 2, din.thresh16) ? dy.z * din.scale : 0.f;
+    dy.w = dropout_keep(bits, 3, din.thresh16) ? dy.w * din.scale : 0.f;
+  }
+  return dy;
+}
+
+__global__ void __launch_bounds__(LNP_THREADS, LNP_CTAS_PER_SM) ln_bwd_pipe_kernel(const LnBwdParams p, int rows_per_block, int stages, int vec_red) {
+  extern __shared__ __align__(128) uint8_t lnp_smem[];
+  pdl_trigger();
+  const int d = p.d, d4 = d >> 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint64_t* full = reinterpret_cast<uint64_t*>(lnp_smem);                  // [stages] (<= 8)
+  float* s_stat = reinterpret_cast<float*>(lnp_smem + 64);                 // [LNP_ROWS][LNP_WPR][4]: s1, s2, mean, rstd partials
+  float* s_gamma = reinterpret_cast<float*>(lnp_smem + 256);               // [d]
+  uint8_t* stage0 = lnp_smem + 256 + ((d * 4 + 127) & ~127);
+  const uint32_t off_dyb = p.dy ? LNP_ROWS * d * 4 : 0;
+  const uint32_t off_pre = off_dyb + (p.dy_b ? LNP_ROWS * d * 2 : 0);
+  const uint32_t stage_bytes = off_pre + LNP_ROWS * d * 4;
+  const int r_begin = blockIdx.x * rows_per_block;
+  const int r_end = min(p.M, r_begin + rows_per_block);
+  const int ntiles = r_end > r_begin ? (r_end - r_begin + LNP_ROWS - 1) / LNP_ROWS : 0;
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  const uint32_t key_in = p.drop_in.thresh16 ? dropout_key(*p.drop_in.seed, p.drop_in.tag) : 0u;
+  const uint32_t key_out = p.drop_out.thresh16 ? dropout_key(*p.drop_out.seed, p.drop_out.tag) : 0u;
+  pdl_wait();
+  for (int i = tid; i < d; i += LNP_THREADS) s_gamma[i] = __ldg(p.gamma + i);
+  __syncthreads();
+
+  auto issue = [&](int tile) {
+    const int s = tile % stages;
+    const int row0 = r_begin + tile * LNP_ROWS;
+    const uint32_t nr = (uint32_t)min(LNP_ROWS, r_end - row0);
+    uint8_t* st = stage0 + (size_t)s * stage_bytes;
+    const uint32_t b4 = nr * d * 4, b2 = nr * d * 2;
+    mbar_arrive_expect_tx(&full[s], (p.dy ? b4 : 0) + (p.dy_b ? b2 : 0) + b4);
+    if (p.dy) bulk_load_1d(st, p.dy + (int64_t)row0 * d, b4, &full[s]);
+    if (p.dy_b) bulk_load_1d(st + off_dyb, p.dy_b + (int64_t)row0 * d, b2, &full[s]);
+    bulk_load_1d(st + off_pre, p.pre + (int64_t)row0 * d, b4, &full[s]);
+  };
+  if (tid == 0)
+    for (int t = 0; t < stages && t < ntiles; ++t) issue(t);
+
+  float4 ag = make_float4(0, 0, 0, 0), ab = ag, az = ag;
+  const bool owner = tid < d4;
+  float4 gm = make_float4(0, 0, 0, 0);
+  if (owner) gm = *reinterpret_cast<const float4*>(s_gamma + 4 * tid);
+  const float inv_d = 1.f / d;
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int s = tile % stages;
+    const uint32_t parity = (uint32_t)(tile / stages) & 1u;
+    const int row0 = r_begin + tile * LNP_ROWS;
+    const int nr = min(LNP_ROWS, r_end - row0);
+    const uint8_t* st = stage0 + (size_t)s * stage_bytes;
+    const float* sdy = p.dy ? reinterpret_cast<const float*>(st) : nullptr;
+    const bf16* sdyb = p.dy_b ? reinterpret_cast<const bf16*>(st + off_dyb) : nullptr;
+    const float* spre = reinterpret_cast<const float*>(st + off_pre);
+    // row statistics of this warp's row are independent of the tile data: fetch them while the copy lands
+    const int ar = warp / LNP_WPR, apart = warp % LNP_WPR;
+    float mean = 0.f, rstd = 0.f;
+    if (ar < nr) { mean = __ldg(p.mean + row0 + ar); rstd = __ldg(p.rstd + row0 + ar); }
+    mbar_wait(&full[s], parity);
+    // ---- phase A: LNP_WPR warps reduce one row (interleaved 32-float4 slices)
+    if (ar < nr) {
+      const int row = row0 + ar;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 3
+      for (int f = apart * 32 + lane; f < d4; f += 32 * LNP_WPR) {
+        const float4 dy = lnp_load_dy(sdy ? sdy + ar * d : nullptr, sdyb ? sdyb + ar * d : nullptr, f, p.drop_in, key_in,
+                                      (uint64_t)row * d4 + f);
+        const float4 x = *reinterpret_cast<const float4*>(spre + ar * d + 4 * f);
+        const float4 g4 = *reinterpret_cast<const float4*>(s_gamma + 4 * f);
+        const float gx = dy.x * g4.x, gy = dy.y * g4.y, gz = dy.z * g4.z, gw = dy.w * g4.w;
+        s1 += gx + gy + gz + gw;
+        s2 += gx * ((x.x - mean) * rstd) + gy * ((x.y - mean) * rstd) + gz * ((x.z - mean) * rstd) + gw * ((x.w - mean) * rstd);
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) *reinterpret_cast<float4*>(s_stat + 4 * warp) = make_float4(s1, s2, mean, rstd);
+    }
+    __syncthreads();
+    // ---- phase B: thread t owns float4 column group t of every row
+    if (owner) {
+#pragma unroll
+      for (int r = 0; r < LNP_ROWS; ++r) {
+        if (r >= nr) break;
+        const int row = row0 + r;
+        float4 stt = *reinterpret_cast<const float4*>(s_stat + 4 * r * LNP_WPR);
+#pragma unroll
+        for (int w = 1; w < LNP_WPR; ++w) {
+          const float4 t2 = *reinterpret_cast<const float4*>(s_stat + 4 * (r * LNP_WPR + w));
+          stt.x += t2.x; stt.y += t2.y;
+        }
+        stt.x *= inv_d; stt.y *= inv_d;
+        const float4 dy = lnp_load_dy(sdy ? sdy + r * d : nullptr, sdyb ? sdyb + r * d : nullptr, tid, p.drop_in, key_in,
+                                      (uint64_t)row * d4 + tid);
+        const float4 x = *reinterpret_cast<const float4*>(spre + r * d + 4 * tid);
+        const float4 xh = make_float4((x.x - stt.z) * stt.w, (x.y - stt.z) * stt.w, (x.z - stt.z) * stt.w, (x.w - stt.z) * stt.w);
+        float4 dx;
+        dx.x = stt.w * (dy.x * gm.x - stt.x - xh.x * stt.y);
+        dx.y = stt.w * (dy.y * gm.y - stt.x - xh.y * stt.y);
+        dx.z = stt.w * (dy.z * gm.z - stt.x - xh.z * stt.y);
+        dx.w = stt.w * (dy.w * gm.w - stt.x - xh.w * stt.y);
+        if (p.dpre) *reinterpret_cast<float4*>(p.dpre + (int64_t)row * d + 4 * tid) = dx;
+        ag.x += dy.x * xh.x; ag.y += dy.y * xh.y; ag.z += dy.z * xh.z; ag.w += dy.w * xh.w;
+        ab.x += dy.x; ab.y += dy.y; ab.z += dy.z; ab.w += dy.w;
+        if (p.dz || p.dbias) {
+          float4 z = dx;
+          if (p.drop_out.thresh16) {
+            const uint64_t bits = dropout_bits4_k(key_out, (uint64_t)row * d4 + tid);
+            z.x = dropout_keep(bits, 0, p.drop_out.thresh16) ? z.x * p.drop_out.scale : 0.f;
+            z.y = dropout_keep(bits, 1, p.drop_out.thresh16) ? z.y * p.drop_out.scale : 0.f;
+            z.z = dropout_keep(bits, 2, p.drop_out.thresh16) ? z.z * p.drop_out.scale : 0.f;
+            z.w = dropout_keep(bits, 3, p.drop_out.thresh16) ? z.w * p.drop_out.scale : 0.f;
+          }
+          if (p.dz) *reinterpret_cast<uint2*>(p.dz + (int64_t)row * d + 4 * tid) = pack4(z);
+          az.x += z.x; az.y += z.y; az.z += z.z; az.w += z.w;
+        }
+      }
+    }
+    __syncthreads();   // every generic read of this stage is done
+    if (tid == 0 && tile + stages < ntiles) {
+      fence_proxy_async_smem();
+      issue(tile + stages);
+    }
+  }
+  if (owner) {
+    const int c = 4 * tid;
+    if (vec_red) {
+      if (p.dgamma) red_add_v4(p.dgamma + c, ag);
+      if (p.dbeta) red_add_v4(p.dbeta + c, ab);
+      if (p.dbias) red_add_v4(p.dbias + c, az);
+    } else {
+      if (p.dgamma) { atomicAdd(p.dgamma + c, ag.x); atomicAdd(p.dgamma + c + 1, ag.y); atomicAdd(p.dgamma + c + 2, ag.z); atomicAdd(p.dgamma + c + 3, ag.w); }
+      if (p.dbeta) { atomicAdd(p.dbeta + c, ab.x); atomicAdd(p.dbeta + c + 1, ab.y); atomicAdd(p.dbeta + c + 2, ab.z); atomicAdd(p.dbeta + c + 3, ab.w); }
+      if (p.dbias) { atomicAdd(p.dbias + c, az.x); atomicAdd(p.dbias + c + 1, az.y); atomicAdd(p.dbias + c + 2, az.z); atomicAdd(p.dbias + c + 3, az.w); }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ embedding backward
 // demb fp32 [M, d] = grad w.r.t. (tok|vis)*scale + pos.  Token rows scatter-add into the shared
 // embedding gradient (skipping padding_idx like nn.Embedding), visual rows are written to
@@ -618,8 +797,37 @@ extern "C" int kmb_layernorm_bwd(const float* dy, const void* dy_bf16, const flo
     kmb_set_last_error("kmb_layernorm_bwd: d_model must be a multiple of 4 and <= 1024", __FILE__, __LINE__);
     return KMB_ERR_ARG;
   }
-  // ~3 blocks per SM: enough loads in flight to saturate HBM while keeping the number of per-block
-  // column-sum atomics (3*d per block) small
+  // bulk-copy pipelined kernel: needs 16-byte aligned operands and rows that are a multiple of 16 bytes in bf16
+  {
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    static int sm_count = 0, smem_optin = 0;
+    if (!sm_count) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+      cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    const size_t stage_bytes = (size_t)LNP_ROWS * d * ((dy ? 4 : 0) + (dy_bf16 ? 2 : 0) + 4);
+    const size_t fixed = 256 + (((size_t)d * 4 + 127) & ~(size_t)127);
+    int stages = (int)((((size_t)smem_optin + 1024) / LNP_CTAS_PER_SM - 2048 - fixed) / stage_bytes);
+    stages = stages > 4 ? 4 : stages;
+    if ((d % 8) == 0 && stages >= 2 && al16(dy) && al16(dy_bf16) && al16(pre) && al16(dpre) && al16(dz_bf16) && al16(gamma)) {
+      const int vec_red = al16(dgamma) && al16(dbeta) && al16(dbias);
+      const int nctas = sm_count * LNP_CTAS_PER_SM;
+      int rpb = (M + nctas - 1) / nctas;
+      const int nblk = (M + rpb - 1) / rpb;
+      const size_t smem = fixed + stages * stage_bytes;
+      static size_t smem_set = 0;
+      if (smem > smem_set) {
+        cudaFuncSetAttribute(ln_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+        smem_set = smem_optin;
+      }
+      launch_pdl(ln_bwd_pipe_kernel, dim3(nblk), dim3(LNP_THREADS), smem, (cudaStream_t)stream, p, rpb, stages, vec_red);
+      KMB_CHECK_LAUNCH();
+      return KMB_OK;
+    }
+  }
+  // fallback (unaligned views): ~3 blocks per SM, scalar atomics
   int rows_per_block = (M + 148 * 3 - 1) / (148 * 3);
   rows_per_block = (rows_per_block + LN_RB - 1) / LN_RB * LN_RB;
   if (rows_per_block < 2 * LN_RB) rows_per_block = 2 * LN_RB;
