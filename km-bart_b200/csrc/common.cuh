@@ -332,7 +332,9 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t ran
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (.release.cta) as in CUTLASS ClusterBarrier::arrive(cta_id): the TMEM reads are ordered by
+  // tcgen05.wait::ld + tcgen05.fence::before_thread_sync; .release.cluster would add a MEMBAR.ALL + ERRBAR per tile
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion bytes are credited to an mbarrier that may live in the peer CTA
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr,

@@ -1,6 +1,6 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a:  D[M,N] = epilogue(sum_k A(m,k) * B(n,k)).
 //
-// One persistent CTA per SM, 384 threads, warp-specialised.  CG = 1: every CTA owns 128 x BN tiles
+// One persistent CTA per SM, GEMM_THREADS (640) threads, warp-specialised.  CG = 1: every CTA owns 128 x BN tiles
 // (tcgen05.mma cta_group::1).  CG = 2: the two CTAs of a 2-CTA cluster own one 256 x BN tile
 // (cta_group::2): each loads its own 128 rows of A and HALF of the B rows, which cuts the
 // bytes an SM has to ingest per flop by a third -- the measured limiter of the single-CTA
@@ -8,7 +8,7 @@
 //   warp 0      TMA producer   (one elected lane; cp.async.bulk.tensor 2D, SWIZZLE_128B)
 //   warp 1      MMA issuer     (one elected lane of the pair's leader CTA; M=128*CG, N=BN, K=16|8)
 //   warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns)
-//   warps 4..11 epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> swizzled smem
+//   warps 4..19 epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> swizzled smem
 //                               transpose -> coalesced global I/O)
 // Three mbarrier pipelines: smem full/empty (TMA<->MMA), tmem full/empty (MMA<->epilogue),
 // and a static round-robin tile schedule.  Operands may be K-major or MN-major (the
@@ -28,6 +28,12 @@
 namespace kmb {
 
 constexpr int BM = 128;
+// Epilogue warps: EPI_SLICES warps per TMEM lane quadrant, each taking every EPI_SLICES-th 32-column chunk of the
+// accumulator.  ncu (profiles/r01f_*): with 2 warps per scheduler the activation / loss epilogues issue at ~0.4 IPC
+// and pace the tensor pipe (fc1+GELU: tensor 34 % active); 4 per scheduler fill the issue slots.
+constexpr int EPI_SLICES = 4;
+constexpr int EPI_WARPS = 4 * EPI_SLICES;
+constexpr int GEMM_THREADS = 128 + 32 * EPI_WARPS;
 constexpr int TILE_BYTES_ROW = 128;  // one swizzle span: 64 bf16 or 32 tf32
 constexpr int A_TILE_BYTES = BM * TILE_BYTES_ROW;
 
@@ -58,11 +64,11 @@ struct Cfg {
   static constexpr int BN_CTA = BN / CG;  // B rows resident in one CTA
   static constexpr int B_TILE_BYTES = BN_CTA * TILE_BYTES_ROW;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int EPI_STAGING = 8 * 4096;  // one 32x32 fp32 transpose tile per epilogue warp
-  static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 256 - EPI_STAGING) / STAGE_BYTES;
+  static constexpr int EPI_STAGING = EPI_WARPS * 4096;  // one 32x32 fp32 transpose tile per epilogue warp
+  static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 512 - EPI_STAGING) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN) <= 32 ? 32 : (2 * BN) <= 64 ? 64 : (2 * BN) <= 128 ? 128 : (2 * BN) <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_STAGING;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + EPI_STAGING;
 };
 
 // Instruction descriptor, field layout per cute/arch/mma_sm100_desc.hpp InstrDescriptor.
@@ -340,7 +346,7 @@ __device__ __forceinline__ void load_bias32(const float* bias, int col0, int N, 
 }
 
 template <int BN, int ELT, int A_MN, int B_MN, int CG>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmPre,
                  const GemmParams p) {
@@ -365,6 +371,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* aux_bars = bars + 2 * STAGES + 5;   // one per epilogue warp: activation-gradient operand tiles (TMA)
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5;
@@ -384,9 +391,10 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&aux_bars[s], 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8 * CG);   // one arrival per epilogue warp of every CTA of the group
+      mbar_init(&tempty_bar[s], EPI_WARPS * CG);   // one arrival per epilogue warp of every CTA of the group
     }
     fence_mbar_init();
   }
@@ -404,6 +412,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
 
+  if (warp < 4) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -484,12 +493,13 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue (8 warps) =====================
-    // warp w may only touch TMEM lanes [32*(w%4), +32); warps 4..7 take even 32-column chunks,
-    // warps 8..11 the odd ones.
+  }
+  } else {
+    // ===================== epilogue (EPI_WARPS warps) =====================
+    // warp w may only touch TMEM lanes [32*(w%4), +32); warps 4..7 take 32-column chunks 0, 4, ...,
+    // warps 8..11 chunks 1, 5, ... and so on.
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int half = (warp - 4) >> 2;   // column slice of this warp: chunks half, half + EPI_SLICES, ...
     float4* st = stage_tiles + (warp - 4) * 256;
     int pp = 0;  // ping-pong index of the TMA-store staging buffers
     int acc = 0;
@@ -497,6 +507,20 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t drop_key = 0;
     if (p.drop_thresh16 && p.e.dropout_seed) drop_key = dropout_key(*p.e.dropout_seed, p.e.dropout_tag);
     const uint32_t tempty_leader0 = CG == 2 ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u;
+    // Activation-gradient epilogues (dX = dY W o act'(aux)): the 32x32 bf16 tile of `aux` that belongs to a chunk is
+    // fetched by TMA (64-byte swizzle, tmPre is encoded over aux in this mode) into the second half of the warp's
+    // staging buffer one chunk ahead -- across tile boundaries too -- so its latency never sits between the TMEM
+    // load and the math; the bf16 output then leaves through the first half only.
+    const bool grad_act = p.e.mode == KMB_EPI_LINEAR && p.tma_out && (p.e.act == KMB_ACT_GELU_GRAD || p.e.act == KMB_ACT_TANH_GRAD);
+    uint64_t* aux_bar = &aux_bars[warp - 4];
+    uint32_t aux_phase = 0;
+    uint4* aux_buf = reinterpret_cast<uint4*>(st) + 128;
+    auto aux_issue = [&](int tt, int cc) {   // lane 0
+      const int mb = tt % p.m_tiles, nb = (tt / p.m_tiles) % p.n_tiles;
+      mbar_arrive_expect_tx(aux_bar, 2048);
+      tma_load_2d(aux_buf, &tmPre, aux_bar, nb * BN + cc * 32, mb * (BM * CG) + (int)cta_rank * BM + q * 32);
+    };
+    if (grad_act && half < BN / 32 && lane == 0 && tile_id0 < total_tiles) aux_issue(tile_id0, half);
     for (int t = tile_id0; t < total_tiles; t += tile_stride) {
       const int m_blk = t % p.m_tiles, n_blk = (t / p.m_tiles) % p.n_tiles;
       const int row0 = m_blk * (BM * CG) + (int)cta_rank * BM + q * 32;
@@ -511,14 +535,35 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       rows_valid = rows_valid > 32 ? 32 : rows_valid;
 
       if (p.e.mode == KMB_EPI_LINEAR && p.tma_out) {
-        // ---- fast path: bias / activation -> bf16 -> TMA store, 32 columns at a time
+        // ---- fast path: bias / activation -> bf16 -> TMA store, 32 columns at a time.  Operands that do not
+        // depend on the accumulator are requested before the TMEM load is awaited: the bias slice (one value per
+        // lane) and, for activation gradients, the aux tile that TMA parked in shared memory a chunk earlier.
         const KmbGemmEpilogue& e = p.e;
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
+        for (int c = half; c < BN / 32; c += EPI_SLICES) {
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
-          tmem_ld_wait();
           const int col0 = n0 + c * 32;
+          uint4 ax[4];
+          if (grad_act) {
+            mbar_wait(aux_bar, aux_phase);
+            aux_phase ^= 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ax[j] = aux_buf[lane * 4 + (j ^ ((lane >> 1) & 3))];
+            __syncwarp();
+            if (lane == 0) {   // the buffer is free again: request the next chunk of this warp
+              const int cn = c + EPI_SLICES;
+              if (cn < BN / 32) aux_issue(t, cn);
+              else if (t + tile_stride < total_tiles) aux_issue(t + tile_stride, half);
+            }
+          }
+          // lane j keeps bias[col0 + j] (one register); it is broadcast with shuffles after the TMEM load has landed
+          float bias_lane = 0.f;
+          if (e.bias) {
+            const int cb = col0 + lane;
+            bias_lane = __ldg(e.bias + (cb < p.N ? cb : p.N - 1));
+          }
+          tmem_ld_wait();
           if (rows_valid > 0 && col0 < p.N) {
             float v[32];
 #pragma unroll
@@ -528,18 +573,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
             }
             if (e.bias) {
-              if (col0 + 32 <= p.N) {
-                const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 t4 = __ldg(b4 + j);
-                  v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.N) v[j] += __ldg(e.bias + col0 + j);
-              }
+              for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
             }
             if (e.act == KMB_ACT_GELU) {
               if (e.out_preact) stage_bf16_chunk_and_store(st, pp, lane, v, &tmPre, col0, row0);
@@ -548,32 +583,34 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             } else if (e.act == KMB_ACT_TANH) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-            } else if (e.act == KMB_ACT_GELU_GRAD || e.act == KMB_ACT_TANH_GRAD) {
-              if (lane == 0) tma_store_wait_read();  // the staging tile doubles as the aux transpose buffer
-              __syncwarp();
-              float a[32];
-              const bf16* ap = reinterpret_cast<const bf16*>(e.aux) + (int64_t)row0 * e.ld_aux + col0;
-              if (col0 + 32 <= p.N && p.vec_ok) {
-                tile_load_bf16(st, lane, ap, e.ld_aux, rows_valid, a);
-              } else {
+            } else if (grad_act) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  a[j] = (row_ok && col0 + j < p.N) ? __bfloat162float(ap[(int64_t)lane * e.ld_aux + j]) : 0.f;
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t w4[4] = {ax[j].x, ax[j].y, ax[j].z, ax[j].w};
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                  const int jj = 8 * j + 2 * l;
+                  const float a0 = __uint_as_float(w4[l] << 16), a1 = __uint_as_float(w4[l] & 0xFFFF0000u);
+                  if (e.act == KMB_ACT_GELU_GRAD) {
+                    v[jj] *= gelu_erf_grad(a0);
+                    v[jj + 1] *= gelu_erf_grad(a1);
+                  } else {
+                    v[jj] *= (1.f - a0 * a0);
+                    v[jj + 1] *= (1.f - a1 * a1);
+                  }
+                }
               }
-              if (e.act == KMB_ACT_GELU_GRAD) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(a[j]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] *= (1.f - a[j] * a[j]);
-              }
+            }
+            if (grad_act) {
+              if (lane == 0) tma_store_wait_read();   // single staging buffer in this mode (the other half holds aux)
+              pp = 0;
             }
             stage_bf16_chunk_and_store(st, pp, lane, v, &tmOut, col0, row0);
           }
         }
       } else if (p.e.mode == KMB_EPI_LINEAR) {
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
+        for (int c = half; c < BN / 32; c += EPI_SLICES) {
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
@@ -589,14 +626,14 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       } else if (p.e.mode == KMB_EPI_CE_STATS) {
         // online softmax partial over this warp's columns of the tile (+ final_logits_bias);
-        // partial index = n_blk * 2 + half.  The bias slice of a chunk is fetched up front as
+        // partial index = n_blk * EPI_SLICES + slice.  The bias slice of a chunk is fetched up front as
         // independent vector loads (a per-column load -> add -> max chain serialises 32 L2 latencies
         // per chunk and made this epilogue 4x longer than the tile's MMA time).
         float mx = -INFINITY, sm = 0.f;
         const int64_t label = row_ok ? p.e.labels[row] : -100;
         constexpr float LOG2E = 1.4426950408889634f;
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
+        for (int c = half; c < BN / 32; c += EPI_SLICES) {
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           const int col0 = n0 + c * 32;
@@ -637,8 +674,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (row_ok) {
-          p.e.ce_max[(int64_t)row * (2 * p.n_tiles) + 2 * n_blk + half] = mx;
-          p.e.ce_sum[(int64_t)row * (2 * p.n_tiles) + 2 * n_blk + half] = sm;
+          p.e.ce_max[(int64_t)row * (EPI_SLICES * p.n_tiles) + EPI_SLICES * n_blk + half] = mx;
+          p.e.ce_sum[(int64_t)row * (EPI_SLICES * p.n_tiles) + EPI_SLICES * n_blk + half] = sm;
         }
       } else {  // KMB_EPI_CE_GRAD: dlogits = (softmax - onehot) * gscale, bf16, through the TMA store path
         const int64_t label = row_ok ? p.e.labels[row] : -100;
@@ -647,7 +684,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         constexpr float LOG2E = 1.4426950408889634f;
         const float a2 = p.e.alpha * LOG2E, nl2 = -lse * LOG2E;
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
+        for (int c = half; c < BN / 32; c += EPI_SLICES) {
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           const int col0 = n0 + c * 32;

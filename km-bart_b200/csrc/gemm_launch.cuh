@@ -35,7 +35,7 @@ static int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int grid = (tiles < groups ? tiles : groups) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(384);
+  cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];

@@ -119,12 +119,12 @@ extern "C" int kmb_gemm_pick_tile_n(int M, int N) {
 }
 
 
-// number of (max, sumexp) partials per row that KMB_EPI_CE_STATS writes: two per n-tile
-// (one per epilogue column half)
+// number of (max, sumexp) partials per row that KMB_EPI_CE_STATS writes: EPI_SLICES per n-tile
+// (one per epilogue column slice)
 extern "C" int kmb_gemm_n_tiles(int N, int tile_n) {
   if (tile_n >= 1000) tile_n -= 1000;
   if (tile_n != 32 && tile_n != 64 && tile_n != 128 && tile_n != 192 && tile_n != 256) return KMB_ERR_ARG;
-  return 2 * ((N + tile_n - 1) / tile_n);
+  return kmb::EPI_SLICES * ((N + tile_n - 1) / tile_n);
 }
 
 extern "C" int kmb_gemm(const void* A, const void* B, int M, int N, int K, int64_t lda, int64_t ldb,
@@ -236,12 +236,18 @@ extern "C" int kmb_gemm(const void* A, const void* B, int M, int N, int K, int64
   p.tma_out = 0;
   const bool lin_fast = epi->mode == KMB_EPI_LINEAR && epi->out_bf16 && !epi->out_f32 && !epi->residual &&
                         epi->dropout_p <= 0.f;
+  const bool grad_act = epi->mode == KMB_EPI_LINEAR && (epi->act == KMB_ACT_GELU_GRAD || epi->act == KMB_ACT_TANH_GRAD);
+  const bool aux_ok = !grad_act || (epi->aux && al16(epi->aux) && (epi->ld_aux % 8) == 0 && !epi->out_preact);
   if ((lin_fast || epi->mode == KMB_EPI_CE_GRAD) && (epi->ld_bf16 % 8) == 0 && al16(epi->out_bf16) &&
-      (!epi->out_preact || al16(epi->out_preact))) {
+      (!epi->out_preact || al16(epi->out_preact)) && aux_ok) {
     rc = make_tmap(&tmOut, epi->out_bf16, 0, (uint64_t)M, (uint64_t)N, (uint64_t)epi->ld_bf16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
     if (epi->out_preact) {
       rc = make_tmap(&tmPre, epi->out_preact, 0, (uint64_t)M, (uint64_t)N, (uint64_t)epi->ld_bf16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
+    if (grad_act) {   // the fast path streams the activation-gradient operand through the tmPre slot
+      rc = make_tmap(&tmPre, epi->aux, 0, (uint64_t)M, (uint64_t)N, (uint64_t)epi->ld_aux, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
     }
     p.tma_out = 1;

@@ -14,6 +14,7 @@ residual stream next to bf16 GEMM operands, fused QKV / cross-KV projections.
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -265,6 +266,10 @@ class Engine:
         e.labels = _ptr(kw.get("labels"))
         e.ce_max, e.ce_sum = _ptr(kw.get("ce_max")), _ptr(kw.get("ce_sum"))
         e.ce_label_logit, e.ce_lse, e.ce_gscale = _ptr(kw.get("ce_label_logit")), _ptr(kw.get("ce_lse")), _ptr(kw.get("ce_gscale"))
+        if os.environ.get("KMBART_DUMP_GEMMS"):   # profiling aid: one line per planned GEMM, in launch order
+            print(f"KMB_GEMM {M} {N} {K} a_mn={a_mn} b_mn={b_mn} mode={e.mode} act={e.act} bias={int(bool(e.bias))} "
+                  f"f32={int(bool(e.out_f32))} b16={int(bool(e.out_bf16))} acc={e.accumulate} res={int(bool(e.residual))} "
+                  f"drop={e.dropout_p}", flush=True)
         plan.add(self.lib.kmb_gemm, _ptr(A), _ptr(B), M, N, K, lda, ldb, a_mn, b_mn, elt, C.byref(e), tile_n,
                  plan.stream, keep=e)
 
