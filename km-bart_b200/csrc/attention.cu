@@ -59,6 +59,11 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float ex2_approx_fwd(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -85,6 +90,21 @@ __device__ __forceinline__ void load_tile_async(bf16* s, const bf16* g, int64_t 
     const uint32_t dst = smem_u32(s + r * LDS + c);
     const int sz = ok ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+  }
+}
+// Same copy with the per-thread (row, 16-byte chunk) pattern hoisted out of the loop: thread t owns chunk t & 7 of
+// rows t >> 3, + nthreads / 8, ... so each request costs two pointer increments instead of 64-bit index arithmetic
+// (the index math of load_tile_async was ~20 % of all instructions of the persistent kernels).
+__device__ __forceinline__ void load_rows_async(bf16* s, const bf16* g, int64_t ld, int nrows, int rows, int tid, int nthreads) {
+  const int c = (tid & 7) * 8, rstep = nthreads >> 3;
+  int r = tid >> 3;
+  const bf16* src = g + (int64_t)r * ld + c;
+  uint32_t dst = smem_u32(s + r * LDS + c);
+  const int64_t sstep = (int64_t)rstep * ld;
+  const uint32_t dstep = (uint32_t)rstep * LDS * 2;
+  for (; r < rows; r += rstep, src += sstep, dst += dstep) {
+    const bool ok = r < nrows;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? src : g), "r"(ok ? 16 : 0) : "memory");
   }
 }
 __device__ __forceinline__ void cp_async_wait_all() {
@@ -233,6 +253,190 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
     float* l = p.lse + ((int64_t)b * p.H + h) * p.Sq;
     if (r_lo < p.Sq) l[r_lo] = mrow[0] + __logf(lrow[0]);
     if (r_lo + 8 < p.Sq) l[r_lo + 8] = mrow[1] + __logf(lrow[1]);
+  }
+}
+
+// ------------------------------------------------------------------ forward, persistent (Sq, Sk <= 128)
+// One persistent 16-warp CTA per SM walks groups of G (batch, head) pairs.  Q, K, V of a group are fetched with
+// cp.async into one of two input buffers while the previous group is computed, each pair's K / V is read from HBM
+// exactly once (the tiled kernel above re-reads them per 64-row query tile and exposes one full load latency per
+// CTA: 21 % of HBM peak at S = 100).  One warp owns 16 query rows of one pair: S = Q K^T for all keys stays in
+// registers (<= 128 keys -> plain two-pass softmax, no online rescale), O = P V, O is staged through the warp's own
+// (already consumed) Q rows in shared memory and leaves as full 128-byte lines.
+constexpr int AF_THREADS = 512;
+constexpr int AF_WARPS = AF_THREADS / 32;
+constexpr int AF_MAXG = 5;
+
+__host__ __device__ inline int af_unit_bytes(int SqP, int SkP) { return (SqP + 2 * SkP) * LDS * 2 + 16; }
+
+template <int NKT>   // 16-key tiles
+__device__ __forceinline__ void af_compute(const AttnParams& p, bf16* sQ, const bf16* sK, const bf16* sV, const uint32_t* bits,
+                                           int qt, int b, int h, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t qf[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+    ldsm_x4(qf[ks], sQ + (qt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8);
+  float s[2 * NKT][4];
+#pragma unroll
+  for (int i = 0; i < 2 * NKT; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+  for (int np = 0; np < NKT; ++np)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t bk[4];
+      ldsm_x4(bk, sK + (np * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + ks * 16 + ((lane >> 3) & 1) * 8);
+      mma16816(s[2 * np], qf[ks], bk[0], bk[1]);
+      mma16816(s[2 * np + 1], qf[ks], bk[2], bk[3]);
+    }
+  // masks: padding / beyond Sk from the bit words, causal from the row index.  An 8-key tile whose mask byte is
+  // clear (and that lies at or below the diagonal for causal attention) takes no per-element work at all.
+  const int r_lo = qt * 16 + g;
+  const float sl2 = p.scale * 1.4426950408889634f;   // scale > 0 (checked on the host)
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int nt = 0; nt < 2 * NKT; ++nt) {
+    const uint32_t byte = (bits[nt >> 2] >> ((nt & 3) * 8)) & 0xFFu;
+    if (byte != 0u || (p.causal && nt * 8 + 7 > qt * 16)) {   // warp-uniform
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int kl = 2 * t + (e & 1);
+        const bool masked = ((byte >> kl) & 1u) || (p.causal && nt * 8 + kl > r_lo + (e >> 1) * 8);
+        if (masked) s[nt][e] = -INFINITY;
+      }
+    }
+    mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+    mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+  }
+  float lsum[2] = {0.f, 0.f}, nm2[2];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+    mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+    nm2[hh] = (mx[hh] == -INFINITY) ? 0.f : -mx[hh] * sl2;   // fully masked row: every p = ex2(-inf) = 0
+  }
+#pragma unroll
+  for (int nt = 0; nt < 2 * NKT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float pv = ex2_approx_fwd(fmaf(s[nt][e], sl2, nm2[e >> 1]));
+      s[nt][e] = pv;
+      lsum[e >> 1] += pv;
+    }
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    lsum[hh] += __shfl_xor_sync(0xffffffffu, lsum[hh], 1);
+    lsum[hh] += __shfl_xor_sync(0xffffffffu, lsum[hh], 2);
+  }
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < NKT; ++ks) {
+    uint32_t a[4];
+    a[0] = pack2(s[2 * ks][0], s[2 * ks][1]);
+    a[1] = pack2(s[2 * ks][2], s[2 * ks][3]);
+    a[2] = pack2(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+    a[3] = pack2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t bv[4];
+      ldsm_x4_t(bv, sV + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + np * 16 + (lane >> 4) * 8);
+      mma16816(o[2 * np], a, bv[0], bv[1]);
+      mma16816(o[2 * np + 1], a, bv[2], bv[3]);
+    }
+  }
+  // a fully masked row yields NaN like the reference's softmax over all -inf (0 * inf)
+  const float inv[2] = {1.f / lsum[0], 1.f / lsum[1]};
+  __syncwarp();   // every lane has fetched its Q fragments: the warp's 16 Q rows become the O staging tile
+  bf16* so = sQ + qt * 16 * LDS;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    *reinterpret_cast<uint32_t*>(so + g * LDS + nt * 8 + 2 * t) = pack2(o[nt][0] * inv[0], o[nt][1] * inv[0]);
+    *reinterpret_cast<uint32_t*>(so + (g + 8) * LDS + nt * 8 + 2 * t) = pack2(o[nt][2] * inv[1], o[nt][3] * inv[1]);
+  }
+  __syncwarp();
+  bf16* og = p.o + b * p.sbo + h * p.sho;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 4 + (lane >> 3), c = (lane & 7) * 8;
+    const int row = qt * 16 + r;
+    if (row < p.Sq) *reinterpret_cast<uint4*>(og + (int64_t)row * p.ldo + c) = *reinterpret_cast<const uint4*>(so + r * LDS + c);
+  }
+  if (p.lse && t == 0) {
+    float* l = p.lse + ((int64_t)b * p.H + h) * p.Sq;
+    // natural-log lse of the scaled scores: (max + log2(sum)) / log2(e)
+    if (r_lo < p.Sq) l[r_lo] = (mx[0] * sl2 + log2f(lsum[0])) * 0.6931471805599453f;
+    if (r_lo + 8 < p.Sq) l[r_lo + 8] = (mx[1] * sl2 + log2f(lsum[1])) * 0.6931471805599453f;
+  }
+}
+
+__global__ void __launch_bounds__(AF_THREADS, 1) attn_fwd_persist_kernel(const AttnParams p, int SqP, int SkP, int G) {
+  pdl_trigger();
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit_bytes = af_unit_bytes(SqP, SkP);
+  const int buf_bytes = G * unit_bytes;
+  const int n_tiles = p.B * p.H;
+  const int n_groups = (n_tiles + G - 1) / G;
+  const int nQ = SqP >> 4, nKT = SkP >> 4;
+  pdl_wait();
+
+  auto issue = [&](int group, int buf) {
+    for (int gi = 0; gi < G; ++gi) {
+      const int tile = group * G + gi;
+      if (tile >= n_tiles) break;
+      const int b = tile / p.H, h = tile % p.H;
+      bf16* sQ = reinterpret_cast<bf16*>(dsm + buf * buf_bytes + gi * unit_bytes);
+      bf16* sK = sQ + SqP * LDS;
+      bf16* sV = sK + SkP * LDS;
+      load_rows_async(sQ, p.q + b * p.sbq + h * p.shq, p.ldq, p.Sq, SqP, threadIdx.x, AF_THREADS);
+      load_rows_async(sK, p.k + b * p.sbk + h * p.shk, p.ldk, p.Sk, SkP, threadIdx.x, AF_THREADS);
+      load_rows_async(sV, p.v + b * p.sbv + h * p.shv, p.ldv, p.Sk, SkP, threadIdx.x, AF_THREADS);
+    }
+    for (int w = warp; w < 4 * G; w += AF_WARPS) {   // key-mask words: bit k of word k/32 set = key k is padding / beyond Sk
+      const int gi = w >> 2, key = (w & 3) * 32 + lane;
+      const int tile = group * G + gi;
+      bool masked = true;
+      if (tile < n_tiles) masked = key >= p.Sk || (p.key_pad && p.key_pad[(int64_t)(tile / p.H) * p.Sk + key]);
+      const uint32_t bits = __ballot_sync(0xffffffffu, masked);
+      if (lane == 0) reinterpret_cast<uint32_t*>(dsm + buf * buf_bytes + gi * unit_bytes + (SqP + 2 * SkP) * LDS * 2)[w & 3] = bits;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  if ((int)blockIdx.x < n_groups) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int group = blockIdx.x; group < n_groups; group += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const bool has_next = group + (int)gridDim.x < n_groups;
+    if (has_next) {
+      issue(group + gridDim.x, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int gi = warp / nQ, qt = warp - gi * nQ;
+    const int tile = group * G + gi;
+    if (gi < G && tile < n_tiles) {
+      bf16* sQ = reinterpret_cast<bf16*>(dsm + buf * buf_bytes + gi * unit_bytes);
+      const bf16* sK = sQ + SqP * LDS;
+      const bf16* sV = sK + SkP * LDS;
+      const uint32_t* bits = reinterpret_cast<const uint32_t*>(dsm + buf * buf_bytes + gi * unit_bytes + (SqP + 2 * SkP) * LDS * 2);
+      const int b = tile / p.H, h = tile % p.H;
+      switch (nKT) {
+        case 1: af_compute<1>(p, sQ, sK, sV, bits, qt, b, h, lane); break;
+        case 2: af_compute<2>(p, sQ, sK, sV, bits, qt, b, h, lane); break;
+        case 3: af_compute<3>(p, sQ, sK, sV, bits, qt, b, h, lane); break;
+        case 4: af_compute<4>(p, sQ, sK, sV, bits, qt, b, h, lane); break;
+        case 5: af_compute<5>(p, sQ, sK, sV, bits, qt, b, h, lane); break;
+        case 6: af_compute<6>(p, sQ, sK, sV, bits, qt, b, h, lane); break;
+        case 7: af_compute<7>(p, sQ, sK, sV, bits, qt, b, h, lane); break;
+        default: af_compute<8>(p, sQ, sK, sV, bits, qt, b, h, lane); break;
+      }
+    }
+    __syncthreads();   // the buffer is refilled by the issue() of the next iteration
   }
 }
 
@@ -739,6 +943,21 @@ static bool attn_bwd_fused_enabled() {
   return !(e && e[0] == '1');
 }
 
+// KMBART_ATTN_FWD_TILED=1 keeps the tiled forward for every shape (A/B timing, tests)
+static bool attn_fwd_persist_enabled() {
+  const char* e = getenv("KMBART_ATTN_FWD_TILED");
+  return !(e && e[0] == '1');
+}
+static int attn_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
 static int check_attn_args(const AttnParams& p) {
   if (!p.q || !p.k || !p.v || p.B <= 0 || p.H <= 0 || p.Sq <= 0 || p.Sk <= 0) return KMB_ERR_ARG;
   if ((p.ldq % 8) || (p.ldk % 8) || (p.ldv % 8)) return KMB_ERR_ARG;
@@ -767,8 +986,32 @@ extern "C" int kmb_attn_fwd(const void* q, const void* k, const void* v, int64_t
     kmb_set_last_error("kmb_attn_fwd: bad argument (head_dim must be 64, strides multiples of 8)", __FILE__, __LINE__);
     return KMB_ERR_ARG;
   }
-  dim3 grid((Sq + TQ - 1) / TQ, H, B);
   if (set_attn_smem_attrs()) return KMB_ERR_CUDA;
+  if (Sq <= 128 && Sk <= 128 && scale > 0.f && attn_fwd_persist_enabled()) {
+    const int SqP = (Sq + 15) & ~15, SkP = (Sk + 15) & ~15;
+    const int nQ = SqP >> 4;
+    int G = AF_WARPS / nQ;
+    G = G > AF_MAXG ? AF_MAXG : G;
+    const int fit = (FB_SMEM_MAX / 2) / af_unit_bytes(SqP, SkP);
+    G = G > fit ? fit : G;
+    if (G >= 1) {
+      static bool attr = false;
+      if (!attr) {
+        if (cudaFuncSetAttribute(attn_fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_MAX) != cudaSuccess) {
+          kmb_set_last_error("attn_fwd_persist_kernel: cannot opt in to 227 KB shared memory", __FILE__, __LINE__);
+          return KMB_ERR_CUDA;
+        }
+        attr = true;
+      }
+      const int n_groups = (B * H + G - 1) / G;
+      const int sms = attn_num_sms();
+      launch_pdl(attn_fwd_persist_kernel, dim3(n_groups < sms ? n_groups : sms), dim3(AF_THREADS), (size_t)2 * G * af_unit_bytes(SqP, SkP),
+                 (cudaStream_t)stream, p, SqP, SkP, G);
+      KMB_CHECK_LAUNCH();
+      return KMB_OK;
+    }
+  }
+  dim3 grid((Sq + TQ - 1) / TQ, H, B);
   launch_pdl(attn_fwd_kernel, dim3(grid), dim3(128), SMEM_FWD, (cudaStream_t)stream, p);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
