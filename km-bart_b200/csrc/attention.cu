@@ -641,6 +641,7 @@ constexpr int FB_THREADS = 512;
 constexpr int FB_WARPS = FB_THREADS / 32;
 constexpr int FB_MAXS = 128;
 constexpr int FB_MAXG = 3;            // (batch, head) pairs processed together when the shapes are small
+static_assert(FB_MAXG <= 3, "the unit -> pair split in attn_bwd_fused_kernel compares against U and 2U");
 constexpr int FB_SMEM_MAX = 232448;   // 227 KB opt-in limit
 
 __host__ __device__ inline int fb_tile_in_bytes(int SqP, int SkP) { return (2 * SqP + 2 * SkP) * LDS * 2; }
@@ -718,6 +719,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const Att
   const int n_groups = (n_tiles + G - 1) / G;
   const int nQ = SqP >> 4, nK = SkP >> 4, nKC = (SkP + 31) >> 5;
   const int nRG = SqP >> 3;   // 8-row groups per tile
+  // reciprocals for the per-unit index splits (exact for the small operands used here: uu < 2^10, tile < 2^31 / H)
+  const uint32_t inv_nKC = (65536u + nKC - 1) / nKC;
+  const uint64_t inv_H = ((1ull << 32) + p.H - 1) / p.H;
   pdl_wait();
 
   auto buf_bits = [&](int buf) { return reinterpret_cast<uint32_t*>(dsm + buf * buf_bytes + G * tile_in); };
@@ -733,10 +737,10 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const Att
       bf16* sdO = sQ + SqP * LDS;
       bf16* sK = sdO + SqP * LDS;
       bf16* sV = sK + SkP * LDS;
-      load_tile_async(sQ, p.q + b * p.sbq + h * p.shq, p.ldq, 0, p.Sq, SqP);
-      load_tile_async(sdO, p.dO + (int64_t)b * p.Sq * p.lddo + h * DH, p.lddo, 0, p.Sq, SqP);
-      load_tile_async(sK, p.k + b * p.sbk + h * p.shk, p.ldk, 0, p.Sk, SkP);
-      load_tile_async(sV, p.v + b * p.sbv + h * p.shv, p.ldv, 0, p.Sk, SkP);
+      load_rows_async(sQ, p.q + b * p.sbq + h * p.shq, p.ldq, p.Sq, SqP, threadIdx.x, FB_THREADS);
+      load_rows_async(sdO, p.dO + (int64_t)b * p.Sq * p.lddo + h * DH, p.lddo, p.Sq, SqP, threadIdx.x, FB_THREADS);
+      load_rows_async(sK, p.k + b * p.sbk + h * p.shk, p.ldk, p.Sk, SkP, threadIdx.x, FB_THREADS);
+      load_rows_async(sV, p.v + b * p.sbv + h * p.shv, p.ldv, p.Sk, SkP, threadIdx.x, FB_THREADS);
     }
     if (warp < 4 * G) {   // key-mask words: bit k of word k/32 set = key k is padding / beyond Sk
       const int gi = warp >> 2, key = (warp & 3) * 32 + lane;
@@ -809,7 +813,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const Att
     // ---------------- phase 1: P and dS tiles (16 query rows x 32 keys per unit)
     const int U1 = nQ * nKC;
     for (int u = warp; u < G * U1; u += FB_WARPS) {
-      const int gi = u / U1, uu = u - gi * U1;
+      const int gi = (u >= U1) + (u >= 2 * U1), uu = u - gi * U1;   // G <= FB_MAXG = 3: no integer division
       if (group * G + gi >= n_tiles) break;
       const bf16* sQ = reinterpret_cast<const bf16*>(bbase + gi * tile_in);
       const bf16* sdO = sQ + SqP * LDS;
@@ -817,7 +821,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const Att
       const bf16* sV = sK + SkP * LDS;
       bf16* sP = sPall + gi * 2 * SqP * LDP;
       bf16* sdS = sP + SqP * LDP;
-      const int qt = uu / nKC, kc = uu - qt * nKC, k0 = kc * 32;
+      const int qt = (int)(((uint32_t)uu * inv_nKC) >> 16), kc = uu - qt * nKC, k0 = kc * 32;
       const int npmax = min(2, (SkP - k0) >> 4);
       const int r_lo = qt * 16 + g;
       float sc[4][4], dp[4][4];
@@ -889,10 +893,10 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const Att
     // ---------------- phase 2: units of 16 rows x 32 head-dim columns: dV, dK per key tile, dQ per query tile
     const int U2 = 2 * (2 * nK + nQ);
     for (int u = warp; u < G * U2; u += FB_WARPS) {
-      const int gi = u / U2, uu = u - gi * U2;
+      const int gi = (u >= U2) + (u >= 2 * U2), uu = u - gi * U2;
       const int tile = group * G + gi;
       if (tile >= n_tiles) break;
-      const int b = tile / p.H, h = tile % p.H;
+      const int b = (int)(((uint64_t)(uint32_t)tile * inv_H) >> 32), h = tile - b * p.H;
       const bf16* sQ = reinterpret_cast<const bf16*>(bbase + gi * tile_in);
       const bf16* sdO = sQ + SqP * LDS;
       const bf16* sK = sdO + SqP * LDS;

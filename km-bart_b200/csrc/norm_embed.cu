@@ -679,6 +679,52 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* x, int64_t
 }
 
 // gather rows: out[i, :] = src[idx[i], :] (bf16), used by the pretraining heads
+// Wide variant: a block covers 256 columns x rows_per_block rows; thread = (8-column group, row phase 0..7), 16-byte
+// loads with eight rows in flight per thread, row phases combined through shared memory, one atomic per column.
+__global__ void __launch_bounds__(256) colsum_bf16_wide_kernel(const bf16* x, int64_t ld, float* out, int M, int N,
+                                                               int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float part[8][256 + 8];
+  const int cg = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + cg * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c < N) {
+    const bf16* px = x + c;
+    for (int r = r0 + rg; r < r1; r += 64) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int rr = r + 8 * u;
+        v[u] = rr < r1 ? __ldg(reinterpret_cast<const uint4*>(px + (int64_t)rr * ld)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] += __uint_as_float(w[j] << 16);
+          acc[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[rg][cg * 8 + j] = acc[j];
+  __syncthreads();
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += part[g][threadIdx.x];
+    atomicAdd(out + col, t);
+  }
+}
+
 __global__ void gather_rows_bf16_kernel(const bf16* src, int64_t ld_src, const int* idx, bf16* out, int64_t ld_out,
                                         int n, int d) {
   const int row = blockIdx.x;
@@ -870,6 +916,15 @@ extern "C" int kmb_colsum_bf16(const void* x, int64_t ld, float* out, int M, int
   if (!x || !out || M <= 0 || N <= 0 || (ld % 2) || (N % 2)) {
     kmb_set_last_error("kmb_colsum_bf16: bad argument", __FILE__, __LINE__);
     return KMB_ERR_ARG;
+  }
+  if ((N % 8) == 0 && (ld % 8) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    // 16-byte loads, 8 rows in flight per thread; enough blocks for ~2 per SM
+    const int cblocks = (N + 255) / 256;
+    int rpb = 256;
+    while (rpb > 32 && cblocks * ((M + rpb - 1) / rpb) < 296) rpb >>= 1;
+    launch_pdl(colsum_bf16_wide_kernel, dim3(cblocks, (M + rpb - 1) / rpb), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, ld, out, M, N, rpb);
+    KMB_CHECK_LAUNCH();
+    return KMB_OK;
   }
   const int rpb = 64;
   launch_pdl(colsum_bf16_kernel, dim3(dim3((N / 2 + 255) / 256, (M + rpb - 1) / rpb)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, ld, out, M, N, rpb);
