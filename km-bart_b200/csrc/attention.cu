@@ -947,10 +947,13 @@ static bool attn_bwd_fused_enabled() {
   return !(e && e[0] == '1');
 }
 
-// KMBART_ATTN_FWD_TILED=1 keeps the tiled forward for every shape (A/B timing, tests)
+// The persistent forward is opt-in (KMBART_ATTN_FWD_PERSIST=1).  Timed alone it beats the tiled kernel (enc 44 vs 58 us,
+// rotating buffers), but inside the train step the tiled kernel's 3072 small CTAs overlap with the neighbouring
+// kernels under programmatic dependent launch while a 193 KB-smem persistent CTA cannot co-reside with a draining GEMM:
+// A/B on the same box, 30 steps: 12.58 / 12.66 ms persistent vs 12.55 / 12.61 ms tiled.  Both paths are parity-tested.
 static bool attn_fwd_persist_enabled() {
-  const char* e = getenv("KMBART_ATTN_FWD_TILED");
-  return !(e && e[0] == '1');
+  const char* e = getenv("KMBART_ATTN_FWD_PERSIST");
+  return e && e[0] == '1';
 }
 static int attn_num_sms() {
   static int n = 0;

@@ -303,12 +303,23 @@ __device__ __forceinline__ void unpack16(const uint4& a, const uint4& b, float (
   for (int i = 0; i < 8; ++i) { f[2 * i] = bf_lo(w[i]); f[2 * i + 1] = bf_hi(w[i]); }
 }
 
+// Memory-level parallelism is the whole game here (one warp, one (row, head), a ~0.7 us L2/HBM round trip per
+// dependent load): both loops request 32 keys per iteration with every load of the batch issued before the first use.
+//   scores: lane = (key phase kq = lane >> 2, 16-dim slice sub = lane & 3): 4 keys x 8 phases in flight
+//   P V   : lane = (key phase kg = lane >> 3, 8-dim slice dc = lane & 7): 16-byte loads, 8 keys x 4 phases in flight,
+//           the four key phases are combined with two shuffles at the end.
+__device__ __forceinline__ uint4 mg_ld16(const bf16* p, bool mut) {
+  return mut ? ldcg16(p) : __ldg(reinterpret_cast<const uint4*>(p));
+}
+
 __device__ void attn_phase(const MgAttn& p, int rows, int H, float* scratch) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sc = scratch + (size_t)warp * MG_MAXT * 2;
   int* sl = reinterpret_cast<int*>(sc + MG_MAXT);
   const int sub = lane & 3, kq = lane >> 2;
+  const int kg = lane >> 3, dc = lane & 7;
   const int units = rows * H;
+  const bool mut = p.kv_mutable;
   for (int u = blockIdx.x + gridDim.x * warp; u < units; u += gridDim.x * MG_WARPS) {
     const int row = u / H, h = u % H;
     float qf[16];
@@ -319,28 +330,45 @@ __device__ void attn_phase(const MgAttn& p, int rows, int H, float* scratch) {
     const int bslot = row / p.row_div;
     const int T = p.T;
     float mx = -INFINITY;
-    for (int pos0 = 0; pos0 < T; pos0 += 8) {
-      const int pos = pos0 + kq;
-      float acc = 0.f;
-      bool ok = pos < T;
-      int slot = bslot;
-      if (ok) {
-        if (p.slot_tbl) slot = __ldg(p.slot_tbl + (int64_t)row * p.tbl_ld + pos);
-        if (p.key_pad && __ldg(p.key_pad + (int64_t)bslot * p.pad_ld + pos)) ok = false;
-      }
-      if (ok) {
-        const bf16* kp = p.k + (int64_t)slot * p.kv_ss + (int64_t)pos * p.kv_ps + h * 64 + sub * 16;
-        float kf[16];
-        if (p.kv_mutable) unpack16(ldcg16(kp), ldcg16(kp + 8), kf);
-        else unpack16(__ldg(reinterpret_cast<const uint4*>(kp)), __ldg(reinterpret_cast<const uint4*>(kp) + 1), kf);
+    for (int pos0 = 0; pos0 < T; pos0 += 32) {
+      bool ok[4];
+      int slot[4];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc = fmaf(qf[j], kf[j], acc);
+      for (int j = 0; j < 4; ++j) {
+        const int pos = pos0 + 8 * j + kq;
+        ok[j] = pos < T;
+        slot[j] = bslot;
+        if (ok[j] && p.slot_tbl) slot[j] = __ldg(p.slot_tbl + (int64_t)row * p.tbl_ld + pos);
       }
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      const float v = ok ? acc * p.scale : -INFINITY;
-      if (sub == 0 && pos < T) { sc[pos] = v; sl[pos] = slot; }
-      mx = fmaxf(mx, v);
+      if (p.key_pad) {
+        uint8_t pd[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pd[j] = ok[j] ? __ldg(p.key_pad + (int64_t)bslot * p.pad_ld + pos0 + 8 * j + kq) : 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ok[j] = ok[j] && !pd[j];
+      }
+      uint4 ka[4], kb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pos = pos0 + 8 * j + kq;
+        const bf16* kp = p.k + (int64_t)slot[j] * p.kv_ss + (int64_t)pos * p.kv_ps + h * 64 + sub * 16;
+        ka[j] = kb[j] = make_uint4(0, 0, 0, 0);
+        if (ok[j]) { ka[j] = mg_ld16(kp, mut); kb[j] = mg_ld16(kp + 8, mut); }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pos = pos0 + 8 * j + kq;
+        float kf[16];
+        unpack16(ka[j], kb[j], kf);
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc = fmaf(qf[i], kf[i], acc);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        const float v = ok[j] ? acc * p.scale : -INFINITY;
+        if (sub == 0 && pos < T) { sc[pos] = v; sl[pos] = slot[j]; }
+        mx = fmaxf(mx, v);
+      }
     }
     mx = warp_max(mx);
     __syncwarp();
@@ -354,18 +382,42 @@ __device__ void attn_phase(const MgAttn& p, int rows, int H, float* scratch) {
     sum = warp_sum(sum);
     __syncwarp();
     const float inv = 1.f / sum;
-    float o0 = 0.f, o1 = 0.f;
-#pragma unroll 4
-    for (int pos = 0; pos < T; ++pos) {
-      const float pr = sc[pos];
-      if (pr != 0.f) {
-        const bf16* vp = p.v + (int64_t)sl[pos] * p.kv_ss + (int64_t)pos * p.kv_ps + h * 64 + 2 * lane;
-        const uint32_t w = p.kv_mutable ? ldcg_u32(vp) : __ldg(reinterpret_cast<const uint32_t*>(vp));
-        o0 = fmaf(pr, bf_lo(w), o0);
-        o1 = fmaf(pr, bf_hi(w), o1);
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0.f;
+    for (int pos0 = 0; pos0 < T; pos0 += 32) {
+      float pr[8];
+      uint4 vv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int pos = pos0 + 4 * j + kg;
+        pr[j] = pos < T ? sc[pos] : 0.f;
+        vv[j] = make_uint4(0, 0, 0, 0);
+        if (pr[j] != 0.f) vv[j] = mg_ld16(p.v + (int64_t)sl[pos] * p.kv_ss + (int64_t)pos * p.kv_ps + h * 64 + dc * 8, mut);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t w[4] = {vv[j].x, vv[j].y, vv[j].z, vv[j].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          o[2 * i] = fmaf(pr[j], bf_lo(w[i]), o[2 * i]);
+          o[2 * i + 1] = fmaf(pr[j], bf_hi(w[i]), o[2 * i + 1]);
+        }
       }
     }
-    *reinterpret_cast<uint32_t*>(p.o + (int64_t)row * p.o_rs + h * 64 + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
+      o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+    }
+    if (kg == 0) {
+      uint4 pk;
+      pk.x = pack_bf16x2(o[0] * inv, o[1] * inv);
+      pk.y = pack_bf16x2(o[2] * inv, o[3] * inv);
+      pk.z = pack_bf16x2(o[4] * inv, o[5] * inv);
+      pk.w = pack_bf16x2(o[6] * inv, o[7] * inv);
+      *reinterpret_cast<uint4*>(p.o + (int64_t)row * p.o_rs + h * 64 + dc * 8) = pk;
+    }
     __syncwarp();
   }
 }

@@ -1,6 +1,6 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a:  D[M,N] = epilogue(sum_k A(m,k) * B(n,k)).
 //
-// One persistent CTA per SM, GEMM_THREADS (640) threads, warp-specialised.  CG = 1: every CTA owns 128 x BN tiles
+// One persistent CTA per SM, 128 + 128 * ES threads (384 or 640), warp-specialised.  CG = 1: every CTA owns 128 x BN tiles
 // (tcgen05.mma cta_group::1).  CG = 2: the two CTAs of a 2-CTA cluster own one 256 x BN tile
 // (cta_group::2): each loads its own 128 rows of A and HALF of the B rows, which cuts the
 // bytes an SM has to ingest per flop by a third -- the measured limiter of the single-CTA
@@ -28,12 +28,14 @@
 namespace kmb {
 
 constexpr int BM = 128;
-// Epilogue warps: EPI_SLICES warps per TMEM lane quadrant, each taking every EPI_SLICES-th 32-column chunk of the
-// accumulator.  ncu (profiles/r01f_*): with 2 warps per scheduler the activation / loss epilogues issue at ~0.4 IPC
-// and pace the tensor pipe (fc1+GELU: tensor 34 % active); 4 per scheduler fill the issue slots.
-constexpr int EPI_SLICES = 4;
-constexpr int EPI_WARPS = 4 * EPI_SLICES;
-constexpr int GEMM_THREADS = 128 + 32 * EPI_WARPS;
+// Epilogue warps: ES ("epilogue slices") warps per TMEM lane quadrant, each taking every ES-th 32-column chunk of the
+// accumulator; a template parameter chosen per launch.  Measured (profiles/r01f_*, build/gemm_test bench):
+//   ES = 2 (8 warps, 384 threads, 168 registers, one more pipeline stage): best for plain bias / bf16-out epilogues,
+//          which hide behind the next tile's MMAs anyway (fc1-shape 1198 vs 1103 TFLOP/s, 8192^3 1330 vs 1198);
+//   ES = 4 (16 warps, 640 threads, 96 registers): activation / activation-gradient / cross-entropy epilogues issue
+//          at ~0.4 IPC with two warps per scheduler and pace the tensor pipe (fc1+GELU: tensor 34 % active); four
+//          per scheduler fill the issue slots (fc1+GELU 84 -> 68 us, GELU-grad 107 -> 75 us).
+constexpr int EPI_SLICES_MAX = 4;   // also the number of cross-entropy partials per n-tile (CE epilogues use ES = 4)
 constexpr int TILE_BYTES_ROW = 128;  // one swizzle span: 64 bf16 or 32 tf32
 constexpr int A_TILE_BYTES = BM * TILE_BYTES_ROW;
 
@@ -59,12 +61,12 @@ struct GemmParams {
   int timeline;
 };
 
-template <int BN, int CG>
+template <int BN, int CG, int ES>
 struct Cfg {
   static constexpr int BN_CTA = BN / CG;  // B rows resident in one CTA
   static constexpr int B_TILE_BYTES = BN_CTA * TILE_BYTES_ROW;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int EPI_STAGING = EPI_WARPS * 4096;  // one 32x32 fp32 transpose tile per epilogue warp
+  static constexpr int EPI_STAGING = 4 * ES * 4096;  // one 32x32 fp32 transpose tile per epilogue warp
   static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 512 - EPI_STAGING) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN) <= 32 ? 32 : (2 * BN) <= 64 ? 64 : (2 * BN) <= 128 ? 128 : (2 * BN) <= 256 ? 256 : 512;
@@ -345,13 +347,15 @@ __device__ __forceinline__ void load_bias32(const float* bias, int col0, int N, 
   }
 }
 
-template <int BN, int ELT, int A_MN, int B_MN, int CG>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int ELT, int A_MN, int B_MN, int CG, int ES>
+__global__ void __launch_bounds__(128 + 128 * ES, 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmPre,
                  const GemmParams p) {
-  using C = Cfg<BN, CG>;
+  using C = Cfg<BN, CG, ES>;
   constexpr int STAGES = C::STAGES;
+  constexpr int EPI_SLICES = ES;
+  constexpr int EPI_WARPS = 4 * ES;
   constexpr int BN_CTA = C::BN_CTA;
   constexpr int ELT_BYTES = ELT == 0 ? 2 : 4;
   constexpr int BK = TILE_BYTES_ROW / ELT_BYTES;  // 64 bf16 / 32 tf32 per k-block

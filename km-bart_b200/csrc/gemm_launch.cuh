@@ -16,11 +16,11 @@ inline int gemm_num_sms() {
   return n;
 }
 
-template <int BN, int ELT, int A_MN, int B_MN, int CG>
-static int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmPre,
+template <int BN, int ELT, int A_MN, int B_MN, int CG, int ES>
+static int gemm_launch_es(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmPre,
                        const GemmParams& p, cudaStream_t st) {
-  using C = Cfg<BN, CG>;
-  auto kern = gemm_tc05_kernel<BN, ELT, A_MN, B_MN, CG>;
+  using C = Cfg<BN, CG, ES>;
+  auto kern = gemm_tc05_kernel<BN, ELT, A_MN, B_MN, CG, ES>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -35,7 +35,7 @@ static int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int grid = (tiles < groups ? tiles : groups) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(128 + 128 * ES);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -60,6 +60,16 @@ static int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     return KMB_ERR_CUDA;
   }
   return KMB_OK;
+}
+
+// epilogue-warp count by epilogue weight (see gemm_kernel.cuh): activations, activation gradients and the
+// cross-entropy epilogues take 16 warps, plain linear epilogues 8
+template <int BN, int ELT, int A_MN, int B_MN, int CG>
+static int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmPre,
+                       const GemmParams& p, cudaStream_t st) {
+  const bool heavy = p.e.mode != KMB_EPI_LINEAR || p.e.act != KMB_ACT_NONE;
+  if (heavy) return gemm_launch_es<BN, ELT, A_MN, B_MN, CG, 4>(tmA, tmB, tmOut, tmPre, p, st);
+  return gemm_launch_es<BN, ELT, A_MN, B_MN, CG, 2>(tmA, tmB, tmOut, tmPre, p, st);
 }
 
 // defined in gemm_pair.cu: CTA-pair (cta_group::2) tiles of 256 x bn, bf16 operands

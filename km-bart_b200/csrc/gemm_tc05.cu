@@ -119,12 +119,12 @@ extern "C" int kmb_gemm_pick_tile_n(int M, int N) {
 }
 
 
-// number of (max, sumexp) partials per row that KMB_EPI_CE_STATS writes: EPI_SLICES per n-tile
-// (one per epilogue column slice)
+// number of (max, sumexp) partials per row that KMB_EPI_CE_STATS writes: EPI_SLICES_MAX per n-tile
+// (one per epilogue column slice; the CE epilogues always run with 16 epilogue warps)
 extern "C" int kmb_gemm_n_tiles(int N, int tile_n) {
   if (tile_n >= 1000) tile_n -= 1000;
   if (tile_n != 32 && tile_n != 64 && tile_n != 128 && tile_n != 192 && tile_n != 256) return KMB_ERR_ARG;
-  return kmb::EPI_SLICES * ((N + tile_n - 1) / tile_n);
+  return kmb::EPI_SLICES_MAX * ((N + tile_n - 1) / tile_n);
 }
 
 extern "C" int kmb_gemm(const void* A, const void* B, int M, int N, int K, int64_t lda, int64_t ldb,
