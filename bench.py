@@ -274,7 +274,11 @@ def run_ours(args):
         gemm_ms = tot / iters
         ach = 2.0 * M * N * K / (gemm_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_tc05_kernel<256> fc1 12800x3072x768", "achieved": round(ach, 1),
-                "peak": burst, "unit": "TFLOP/s", "frac": round(ach / burst, 4), "traffic": None,
+                "peak": burst, "unit": "TFLOP/s", "frac": round(ach / burst, 4),
+                # DRAM bytes of ONE launch of this kernel from the ncu --set full capture committed as
+                # profiles/r01k_ncu_gemm_fc1_plain_summary.txt (dram__bytes_read.sum 24.75 MB + dram__bytes_write.sum
+                # 32.03 MB; algorithmic: 24.4 MB operands + 78.6 MB output, most of which is still dirty in L2 at kernel end)
+                "traffic": 56780288, "traffic_unit": "bytes/launch (ncu, profiles/r01k_ncu_gemm_fc1_plain_summary.txt)",
                 "peak_source": peak_src + " burst (kernel timed alone, L2 flushed between launches)",
                 "step_mfu": None}
 

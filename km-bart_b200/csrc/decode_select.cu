@@ -9,14 +9,37 @@
 namespace kmb {
 
 // one CTA per row: argmax over V fp32 logits (first index on ties, like torch.argmax), then the bookkeeping
-__global__ void __launch_bounds__(256) greedy_select_kernel(const float* logits, int64_t ld, int V, int eos, int pad, int ban_eos,
+__global__ void __launch_bounds__(1024) greedy_select_kernel(const float* logits, int64_t ld, int V, int eos, int pad, int ban_eos,
                                                             int cur_len, int64_t* unfinished, int64_t* sent_len, int64_t* out,
                                                             int64_t out_ld, int64_t* ids_next) {
   const int row = blockIdx.x;
   const float* x = logits + (int64_t)row * ld;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int i = threadIdx.x * 4; i < V; i += blockDim.x * 4) {
+  auto consume = [&](const float (&v)[4], int i) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float val = v[j];
+      if (ban_eos && i + j == eos) val = -INFINITY;
+      if (i + j < V && (val > best || (val == best && i + j < bi))) { best = val; bi = i + j; }
+    }
+  };
+  const int stride = blockDim.x * 4;
+  int i = threadIdx.x * 4;
+  if ((((uintptr_t)x) & 15) == 0) {
+    // four independent 16-byte loads in flight per thread (the row is a 200 KB latency-bound stream for one CTA)
+    for (; i + 3 * stride + 4 <= V; i += 4 * stride) {
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = *reinterpret_cast<const float4*>(x + i + u * stride);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float v[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+        consume(v, i + u * stride);
+      }
+    }
+  }
+  for (; i < V; i += stride) {
     float v[4];
     if (i + 4 <= V && ((((uintptr_t)(x + i)) & 15) == 0)) {
       const float4 t = *reinterpret_cast<const float4*>(x + i);
@@ -25,12 +48,7 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* logits,
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = (i + j < V) ? x[i + j] : -INFINITY;
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float val = v[j];
-      if (ban_eos && i + j == eos) val = -INFINITY;
-      if (i + j < V && (val > best || (val == best && i + j < bi))) { best = val; bi = i + j; }
-    }
+    consume(v, i);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -38,8 +56,8 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* logits,
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
   }
-  __shared__ float sb[8];
-  __shared__ int si[8];
+  __shared__ float sb[32];
+  __shared__ int si[32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   if (lane == 0) { sb[wib] = best; si[wib] = bi; }
   __syncthreads();
@@ -70,7 +88,7 @@ extern "C" int kmb_greedy_select(const float* logits, int64_t ld, int rows, int 
     kmb_set_last_error("kmb_greedy_select: bad argument", __FILE__, __LINE__);
     return KMB_ERR_ARG;
   }
-  kmb::greedy_select_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, V, eos_token_id, pad_token_id, ban_eos, cur_len,
+  kmb::greedy_select_kernel<<<rows, 1024, 0, (cudaStream_t)stream>>>(logits, ld, V, eos_token_id, pad_token_id, ban_eos, cur_len,
                                                                     unfinished, sent_len, out_tokens, out_ld, ids_next);
   KMB_CHECK_LAUNCH();
   return KMB_OK;

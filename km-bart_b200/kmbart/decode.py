@@ -127,7 +127,10 @@ class DecodeSession:
         if self.mega:
             args = self._mega_args(t)
             plan.add(lib.kmb_decode_step, ctypes.byref(args), plan.stream, keep=args)
-            eng.gemm(plan, self.x_b16[0], st.p16(eng.n("shared.weight")), rows, V, d, d, d, bias=self.flb, out_f32=self.logits, ld_f32=V)
+            # LM head at M <= 128 is a pure weight stream (77 MB): narrow single-CTA tiles cut the wave-quantisation
+            # loss of 197 tiles of 256 columns on 148 SMs (2 waves, the second a third full)
+            eng.gemm(plan, self.x_b16[0], st.p16(eng.n("shared.weight")), rows, V, d, d, d, bias=self.flb, out_f32=self.logits, ld_f32=V,
+                     tile_n=int(os.environ.get("KMBART_LMHEAD_TILE", "128")) if rows <= 128 else 0)
             return
         scale = math.sqrt(d) if cfg.scale_embedding else 1.0
         x_f32, x_b16 = self.x_f32[0], self.x_b16[0]

@@ -216,6 +216,23 @@ int main(int argc, char** argv) {
     bench_case(8192, 8192, 8192, 0, 0, 256, "big");
     return 0;
   }
+  if (argc > 1 && !strcmp(argv[1], "bench3")) {   // CTA-pair tile widths per shape, plain and GELU epilogues
+    for (int mode = 1; mode < 3; ++mode) {
+      g_noout = 0; g_gelu = mode == 2;
+      printf("--- mode %s\n", mode == 1 ? "bf16 out" : "gelu + preact + bf16 out");
+      for (int tn : {0, 1128, 1192, 1256}) {
+        bench_case(12800, 3072, 768, 0, 0, tn, "fc1");
+        bench_case(6144, 3072, 768, 0, 0, tn, "fc1_dec");
+        if (mode == 1) {
+          bench_case(12800, 2304, 768, 0, 0, tn, "qkv");
+          bench_case(12800, 768, 3072, 0, 0, tn, "fc2");
+          bench_case(6144, 768, 768, 0, 0, tn, "proj_dec");
+          bench_case(12800, 768, 768, 0, 0, tn, "proj_enc");
+        }
+      }
+    }
+    return 0;
+  }
   if (argc > 1 && !strcmp(argv[1], "bench")) {
     bench_case(12800, 768, 768, 0, 0, 0, "proj");
     bench_case(12800, 768, 768, 0, 0, 128, "proj128");
