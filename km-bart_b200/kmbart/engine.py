@@ -19,6 +19,7 @@ import os
 import torch
 
 from . import lib as L
+from .feed import unwrap_features
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -688,6 +689,7 @@ class Engine:
     # ------------------------------------------------------------------ public: training step pieces
     def train_forward(self, input_ids, image_features, attention_mask, decoder_input_ids, decoder_attention_mask, labels,
                       final_logits_bias, training, lm_factor=1.0, image_counts=None, with_heads=False):
+        image_features, image_counts = unwrap_features(image_features, image_counts)   # kmbart.feed.PackedImageFeatures
         self.sync_shadow()
         a, key = self._get_arena("train", input_ids, image_features, attention_mask, decoder_input_ids, labels, training,
                                  lm_factor, image_counts, has_lm=labels is not None, with_heads=with_heads)
@@ -728,6 +730,7 @@ class Engine:
     def infer_forward(self, input_ids, image_features, attention_mask, decoder_input_ids, decoder_attention_mask,
                       encoder_only=False, image_counts=None):
         """Full-sequence forward without stashing; returns (enc_f32 [B,Se,d], dec_f32 [B,Sd,d] or None, arena)."""
+        image_features, image_counts = unwrap_features(image_features, image_counts)
         self.sync_shadow()
         a, key = self._get_arena("enc" if encoder_only else "infer", input_ids, image_features, attention_mask,
                                  None if encoder_only else decoder_input_ids, None, False, 1.0, image_counts)

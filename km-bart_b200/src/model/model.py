@@ -209,6 +209,8 @@ def _core_forward_fp32(owner, input_ids, image_features, attention_mask, decoder
                        decoder_attention_mask, decoder_cached_states, use_cache):
     """fp32 parity mode of _core_forward: same control flow, kernels from kmbart/fp32.py (hidden states stay fp32)."""
     cfg = owner.config
+    if hasattr(image_features, "as_list"):   # kmbart.feed.PackedImageFeatures
+        image_features = image_features.as_list()
     fp = owner._fp32()
     if encoder_outputs is None:
         enc = fp.encoder(input_ids, image_features, attention_mask)

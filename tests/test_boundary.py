@@ -213,3 +213,23 @@ def test_param_store_layout(small_model):
     o = st.offsets["model.decoder.layers.0.encoder_attn.k_proj.weight"]
     assert st.offsets["model.decoder.layers.0.encoder_attn.v_proj.weight"] == o + d * d
     assert st.offsets["model.shared.weight"] == st.zero_end and st.is_adopted()
+
+
+def test_packed_image_features_is_list_like():
+    """kmbart.feed.PackedImageFeatures stands in for the reference's list of per-sample RoI tensors
+    (src/data/collation.py:68-213 output, src/training.py:120-130 consumer): len / index / iteration give views."""
+    import torch
+    from kmbart.feed import PackedImageFeatures, unwrap_features
+    t = torch.arange(5 * 2052, dtype=torch.float32).view(5, 2052)
+    pf = PackedImageFeatures(t, [2, 0, 3])
+    assert len(pf) == 3
+    parts = pf.as_list()
+    assert [p.shape[0] for p in parts] == [2, 0, 3]
+    assert parts[2].data_ptr() == t[2:].data_ptr() and torch.equal(pf[0], t[:2])
+    ft, counts = unwrap_features(pf)
+    assert ft is t and counts == [2, 0, 3]
+    lst = [t[:2], t[2:]]
+    assert unwrap_features(lst) == (lst, None)
+    import pytest
+    with pytest.raises(AssertionError):
+        PackedImageFeatures(t, [1, 1])

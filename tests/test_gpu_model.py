@@ -589,3 +589,50 @@ def test_persistent_decode_step_small_model_vs_oracle(fwd_setup):
     sessions = [s for k, s in eng.arenas.items() if isinstance(k, tuple) and k and k[0] == "dec"]
     assert sessions and all(s.mega for s in sessions)
     assert _near_tie_ok(sd, ocfg, batch, toks, 2e-2)
+
+
+# ------------------------------------------------------------------ batch feed
+def test_device_feeder_matches_list_api(fwd_setup):
+    """DeviceFeeder (pinned host batch -> side-stream copies into one staging buffer -> PackedImageFeatures) gives the
+    same loss, gradients and generations as the reference's list-of-tensors `.to(device)` path
+    (src/training.py:120-130), across slot rotation and with a ragged / empty feature list."""
+    from kmbart.feed import DeviceFeeder, PackedImageFeatures
+    ocfg, sd, _, _ = fwd_setup
+    model = make_model(ocfg, sd, train=True)
+    hosts = []
+    for i in range(4):
+        b = O.synthetic_batch(ocfg, batch=3, n_regions=4, n_ctx=10, tgt_len=6, seed=20 + i, ragged=(i % 2 == 1))
+        if i == 2:
+            b["image_features"][1] = torch.zeros(0, 2052)
+            b["input_ids"][1][b["input_ids"][1] == ocfg.img_feat_id] = 7
+        hosts.append({k: ([t.pin_memory() for t in v] if isinstance(v, list) else v.pin_memory()) for k, v in b.items()})
+    ref = []
+    for hb in hosts:
+        model.zero_grad()
+        loss = model(**to_cuda_batch(hb))[0]
+        loss.backward()
+        ref.append((loss.item(), model.model.encoder.embed_images.linear.weight.grad.clone()))
+    feeder = DeviceFeeder("cuda", depth=2)
+    got = []
+    for b in feeder(hosts):
+        assert isinstance(b["image_features"], PackedImageFeatures) and len(b["image_features"]) == 3
+        model.zero_grad()
+        loss = model(**b)[0]
+        loss.backward()
+        got.append((loss.item(), model.model.encoder.embed_images.linear.weight.grad.clone()))
+    assert len(got) == len(ref)
+    for (l0, g0), (l1, g1) in zip(ref, got):
+        assert l0 == l1                      # same kernels on the same bytes: bit-identical
+        assert torch.equal(g0, g1)
+    # generation through the packed features
+    model.eval()
+    feeder.put(hosts[0])
+    b = feeder.get()
+    cb = to_cuda_batch(hosts[0])
+    with torch.no_grad():
+        t_list = model.generate(input_ids=cb["input_ids"], image_features=cb["image_features"], attention_mask=cb["attention_mask"], max_length=6)
+        t_pack = model.generate(input_ids=b["input_ids"], image_features=b["image_features"], attention_mask=b["attention_mask"], max_length=6)
+    feeder.release()
+    assert torch.equal(t_list, t_pack)
+    with pytest.raises(RuntimeError):
+        feeder.get()                          # nothing pending
