@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
   bf16* sQ = reinterpret_cast<bf16*>(dsm);
   bf16* sK = sQ + TQ * LDS;
   bf16* sV = sK + SB * LDS;
-  uint8_t* sPad = reinterpret_cast<uint8_t*>(sV + SB * LDS);
+  uint32_t* sBits = reinterpret_cast<uint32_t*>(sV + SB * LDS);   // 4 words: bit k set = resident key k is padding / beyond Sk
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
   const bf16* qg = p.q + b * p.sbq + h * p.shq;
@@ -180,18 +180,23 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
   float o[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  // running row maximum of the RAW scores (scale > 0 is folded into the exponent: one FFMA + ex2 per element)
   float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+  const float sl2 = p.scale * 1.4426950408889634f;
   const int r_lo = q0 + warp * 16 + g;
+  const int w_row0 = q0 + warp * 16;     // first query row of this warp (causal tile test)
   int kend = p.Sk;
   if (p.causal && q0 + TQ < kend) kend = q0 + TQ;
   for (int kk0 = 0; kk0 < kend; kk0 += SB) {
     __syncthreads();
-    if (kk0 == 0) load_tile_async(sQ, qg, p.ldq, q0, p.Sq, TQ);
-    load_tile_async(sK, kg, p.ldk, kk0, p.Sk, SB);
-    load_tile_async(sV, vg, p.ldv, kk0, p.Sk, SB);
-    if (threadIdx.x < SB) {
-      const int c = kk0 + threadIdx.x;
-      sPad[threadIdx.x] = (c >= p.Sk) ? 1 : (p.key_pad ? p.key_pad[(int64_t)b * p.Sk + c] : 0);
+    if (kk0 == 0) load_rows_async(sQ, qg + (int64_t)q0 * p.ldq, p.ldq, p.Sq - q0, TQ, threadIdx.x, 128);
+    load_rows_async(sK, kg + (int64_t)kk0 * p.ldk, p.ldk, p.Sk - kk0, SB, threadIdx.x, 128);
+    load_rows_async(sV, vg + (int64_t)kk0 * p.ldv, p.ldv, p.Sk - kk0, SB, threadIdx.x, 128);
+    {
+      const int c = kk0 + threadIdx.x;   // 128 threads = the SB resident keys
+      const bool masked = c >= p.Sk || (p.key_pad && p.key_pad[(int64_t)b * p.Sk + c]);
+      const uint32_t bits = __ballot_sync(0xffffffffu, masked);
+      if (lane == 0) sBits[warp] = bits;
     }
     cp_async_wait_all();
     __syncthreads();
@@ -200,31 +205,36 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
     for (int k0 = kk0; k0 < kstop; k0 += TK) {
       const bf16* sKb = sK + (k0 - kk0) * LDS;
       const bf16* sVb = sV + (k0 - kk0) * LDS;
-      const uint8_t* sPb = sPad + (k0 - kk0);
+      const uint32_t wbits[2] = {sBits[(k0 - kk0) >> 5], sBits[((k0 - kk0) >> 5) + 1]};
       float s[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
       mma_a_yt(s, qf, sKb, lane);
       float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < 8; ++nt) {
+        const uint32_t byte = (wbits[nt >> 2] >> ((nt & 3) * 8)) & 0xFFu;
+        if (byte != 0u || (p.causal && k0 + nt * 8 + 7 > w_row0)) {   // warp-uniform: clean tiles take no mask work
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int cl = nt * 8 + 2 * t + (e & 1);
-          const int row = r_lo + (e >> 1) * 8;
-          const bool masked = sPb[cl] || (p.causal && (k0 + cl) > row);
-          const float v = masked ? -INFINITY : s[nt][e] * p.scale;
-          s[nt][e] = v;
-          mx[e >> 1] = fmaxf(mx[e >> 1], v);
+          for (int e = 0; e < 4; ++e) {
+            const int kl = 2 * t + (e & 1);
+            const bool masked = ((byte >> kl) & 1u) || (p.causal && k0 + nt * 8 + kl > r_lo + (e >> 1) * 8);
+            if (masked) s[nt][e] = -INFINITY;
+          }
         }
-      float corr[2], mnew[2];
+        mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+      }
+      float corr[2], nm2[2];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
         mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
-        mnew[hh] = fmaxf(mrow[hh], mx[hh]);
-        corr[hh] = (mnew[hh] == -INFINITY) ? 1.f : __expf(mrow[hh] - mnew[hh]);
-        mrow[hh] = mnew[hh];
+        const float mnew = fmaxf(mrow[hh], mx[hh]);
+        const bool dead = mnew == -INFINITY;          // every key so far masked: p = 0, nothing to rescale
+        corr[hh] = dead ? 1.f : ex2_approx_fwd((mrow[hh] - mnew) * sl2);
+        nm2[hh] = dead ? 0.f : -mnew * sl2;
+        mrow[hh] = mnew;
         lrow[hh] *= corr[hh];
       }
 #pragma unroll
@@ -232,7 +242,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int hh = e >> 1;
-          const float pv = (mnew[hh] == -INFINITY) ? 0.f : __expf(s[nt][e] - mnew[hh]);
+          const float pv = ex2_approx_fwd(fmaf(s[nt][e], sl2, nm2[hh]));   // s = -inf -> 0
           s[nt][e] = pv;
           lrow[hh] += pv;
           o[nt][e] *= corr[hh];
@@ -251,8 +261,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
   store_rows(og, p.ldo, r_lo, p.Sq, o, lane, inv_lo, inv_hi);
   if (p.lse && t == 0) {
     float* l = p.lse + ((int64_t)b * p.H + h) * p.Sq;
-    if (r_lo < p.Sq) l[r_lo] = mrow[0] + __logf(lrow[0]);
-    if (r_lo + 8 < p.Sq) l[r_lo + 8] = mrow[1] + __logf(lrow[1]);
+    if (r_lo < p.Sq) l[r_lo] = (mrow[0] * sl2 + log2f(lrow[0])) * 0.6931471805599453f;
+    if (r_lo + 8 < p.Sq) l[r_lo + 8] = (mrow[1] * sl2 + log2f(lrow[1])) * 0.6931471805599453f;
   }
 }
 
@@ -967,6 +977,7 @@ static int attn_num_sms() {
 
 static int check_attn_args(const AttnParams& p) {
   if (!p.q || !p.k || !p.v || p.B <= 0 || p.H <= 0 || p.Sq <= 0 || p.Sk <= 0) return KMB_ERR_ARG;
+  if (!(p.scale > 0.f)) return KMB_ERR_ARG;   // the kernels track the maximum of the raw scores and fold the scale into the exponent
   if ((p.ldq % 8) || (p.ldk % 8) || (p.ldv % 8)) return KMB_ERR_ARG;
   return KMB_OK;
 }

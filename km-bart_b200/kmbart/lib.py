@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libkmbart_sm100.so")
+# KMBART_LIB_PATH: an alternative build of the same library (A/B timing of kernel variants on one box)
+LIB_PATH = os.environ.get("KMBART_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "libkmbart_sm100.so")
 
 c_void_p, c_int, c_int64, c_float, c_uint32 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32
 

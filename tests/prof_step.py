@@ -10,11 +10,20 @@ from src.model.model import MultiModalBartForConditionalGeneration
 from kmbart.optim import AdamW
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-cfg = MultiModalBartConfig.from_dict(json.load(open(os.path.join(ROOT, "configs", "vcg_base.json"))))
+large = len(sys.argv) > 2 and sys.argv[2] == "large"   # BASELINE configs[4] shapes, batch 64
+if large:
+    cfg = MultiModalBartConfig(max_position_embeddings=1024)
+else:
+    cfg = MultiModalBartConfig.from_dict(json.load(open(os.path.join(ROOT, "configs", "vcg_base.json"))))
 torch.manual_seed(0)
 model = MultiModalBartForConditionalGeneration(cfg).cuda().train()
 opt = AdamW(model.parameters(), lr=1e-5)
-batch = bench.make_batch(cfg, 1234, device="cuda")
+if large:
+    from oracle import kmbart_oracle as O   # synthetic-batch generator only
+    b = O.synthetic_batch(cfg, batch=64, n_regions=100, n_ctx=256, tgt_len=48, seed=1234)
+    batch = {k: ([t.cuda() for t in v] if isinstance(v, list) else v.cuda()) for k, v in b.items()}
+else:
+    batch = bench.make_batch(cfg, 1234, device="cuda")
 
 def step():
     loss = model(**batch)[0]

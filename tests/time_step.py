@@ -9,11 +9,22 @@ from src.model.model import MultiModalBartForConditionalGeneration
 from kmbart.optim import AdamW
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-cfg = MultiModalBartConfig.from_dict(json.load(open(os.path.join(ROOT, "configs", "vcg_base.json"))))
+large = len(sys.argv) > 2 and sys.argv[2] == "large"   # BASELINE configs[4]: d=1024 12+12, 100 RoIs + 256 ctx tokens, batch 64/GPU
+if large:
+    from oracle import kmbart_oracle as O   # synthetic-batch generator only
+    cfg = MultiModalBartConfig(max_position_embeddings=1024)
+    BATCH, FLOP_PER_SAMPLE = 64, 464.662e9
+else:
+    cfg = MultiModalBartConfig.from_dict(json.load(open(os.path.join(ROOT, "configs", "vcg_base.json"))))
+    BATCH, FLOP_PER_SAMPLE = 128, 56.412e9
 torch.manual_seed(0)
 model = MultiModalBartForConditionalGeneration(cfg).cuda().train()
 opt = AdamW(model.parameters(), lr=1e-5)
-batch = bench.make_batch(cfg, 1234, device="cuda")
+if large:
+    b = O.synthetic_batch(cfg, batch=BATCH, n_regions=100, n_ctx=256, tgt_len=48, seed=1234)
+    batch = {k: ([t.cuda() for t in v] if isinstance(v, list) else v.cuda()) for k, v in b.items()}
+else:
+    batch = bench.make_batch(cfg, 1234, device="cuda")
 
 def step():
     loss = model(**batch)[0]
@@ -32,7 +43,8 @@ for _ in range(steps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
-print(f"train step {ms:.3f} ms  ({128 / ms * 1e3:.0f} samples/s)  loss {loss.item():.5f}  PDL={'off' if os.environ.get('KMBART_NO_PDL') == '1' else 'on'}")
+print(f"train step {ms:.3f} ms  ({BATCH / ms * 1e3:.0f} samples/s, {BATCH * FLOP_PER_SAMPLE / ms / 1e9:.0f} TFLOP/s)  loss {loss.item():.5f}  "
+      f"PDL={'off' if os.environ.get('KMBART_NO_PDL') == '1' else 'on'}  config={'large d=1024 12+12 S_e=356 B=64' if large else 'base B=128'}")
 import time
 torch.cuda.synchronize()
 t0 = time.perf_counter()
