@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
   bf16* sdO = sQ + TQ * LDS;
   bf16* sK = sdO + TQ * LDS;
   bf16* sV = sK + SB * LDS;
-  uint8_t* sPad = reinterpret_cast<uint8_t*>(sV + SB * LDS);
+  uint32_t* sBits = reinterpret_cast<uint32_t*>(sV + SB * LDS);   // bit k set = resident key k is padding / beyond Sk
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
   const bf16* qg = p.q + b * p.sbq + h * p.shq;
@@ -485,13 +485,19 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
   const bf16* dog = p.dO + (int64_t)b * p.Sq * p.lddo + h * DH;
   uint32_t qf[4][4], dof[4][4];
   const int r_lo = q0 + warp * 16 + g;
+  const int w_row0 = q0 + warp * 16;
   const float* lse = p.lse + ((int64_t)b * p.H + h) * p.Sq;
   const float* Dg = p.D + ((int64_t)b * p.H + h) * p.Sq;
-  float lrow[2], drow[2];
-  lrow[0] = r_lo < p.Sq ? lse[r_lo] : -INFINITY;
-  lrow[1] = r_lo + 8 < p.Sq ? lse[r_lo + 8] : -INFINITY;
-  drow[0] = r_lo < p.Sq ? Dg[r_lo] : 0.f;
-  drow[1] = r_lo + 8 < p.Sq ? Dg[r_lo + 8] : 0.f;
+  // per-row constants in the log2 domain: P = ex2(s*scale*log2e + nl); a dead row (lse = -inf) gets nl = -inf -> P = 0
+  const float sl2 = p.scale * 1.4426950408889634f;
+  float nl[2], dsc[2];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int r = r_lo + hh * 8;
+    const float l = r < p.Sq ? lse[r] : -INFINITY;
+    nl[hh] = l == -INFINITY ? -INFINITY : -l * 1.4426950408889634f;
+    dsc[hh] = (r < p.Sq ? Dg[r] : 0.f) * p.scale;
+  }
   float dq[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
@@ -500,14 +506,16 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
   for (int kk0 = 0; kk0 < kend; kk0 += SB) {
     __syncthreads();
     if (kk0 == 0) {
-      load_tile_async(sQ, qg, p.ldq, q0, p.Sq, TQ);
-      load_tile_async(sdO, dog, p.lddo, q0, p.Sq, TQ);
+      load_rows_async(sQ, qg + (int64_t)q0 * p.ldq, p.ldq, p.Sq - q0, TQ, threadIdx.x, 128);
+      load_rows_async(sdO, dog + (int64_t)q0 * p.lddo, p.lddo, p.Sq - q0, TQ, threadIdx.x, 128);
     }
-    load_tile_async(sK, kg, p.ldk, kk0, p.Sk, SB);
-    load_tile_async(sV, vg, p.ldv, kk0, p.Sk, SB);
-    if (threadIdx.x < SB) {
+    load_rows_async(sK, kg + (int64_t)kk0 * p.ldk, p.ldk, p.Sk - kk0, SB, threadIdx.x, 128);
+    load_rows_async(sV, vg + (int64_t)kk0 * p.ldv, p.ldv, p.Sk - kk0, SB, threadIdx.x, 128);
+    {
       const int c = kk0 + threadIdx.x;
-      sPad[threadIdx.x] = (c >= p.Sk) ? 1 : (p.key_pad ? p.key_pad[(int64_t)b * p.Sk + c] : 0);
+      const bool masked = c >= p.Sk || (p.key_pad && p.key_pad[(int64_t)b * p.Sk + c]);
+      const uint32_t bits = __ballot_sync(0xffffffffu, masked);
+      if (lane == 0) sBits[warp] = bits;
     }
     cp_async_wait_all();
     __syncthreads();
@@ -519,7 +527,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
     for (int k0 = kk0; k0 < kstop; k0 += TK) {
       const bf16* sKb = sK + (k0 - kk0) * LDS;
       const bf16* sVb = sV + (k0 - kk0) * LDS;
-      const uint8_t* sPb = sPad + (k0 - kk0);
+      const uint32_t wbits[2] = {sBits[(k0 - kk0) >> 5], sBits[((k0 - kk0) >> 5) + 1]};
       float s[8][4], dp[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -529,16 +537,22 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
       mma_a_yt(s, qf, sKb, lane);
       mma_a_yt(dp, dof, sVb, lane);
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < 8; ++nt) {
+        const uint32_t byte = (wbits[nt >> 2] >> ((nt & 3) * 8)) & 0xFFu;
+        if (byte != 0u || (p.causal && k0 + nt * 8 + 7 > w_row0)) {   // warp-uniform
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int kl = 2 * t + (e & 1);
+            if (((byte >> kl) & 1u) || (p.causal && k0 + nt * 8 + kl > r_lo + (e >> 1) * 8)) s[nt][e] = -INFINITY;
+          }
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int cl = nt * 8 + 2 * t + (e & 1);
           const int hh = e >> 1;
-          const int row = r_lo + hh * 8;
-          const bool masked = sPb[cl] || (p.causal && (k0 + cl) > row) || lrow[hh] == -INFINITY;
-          const float pv = masked ? 0.f : __expf(s[nt][e] * p.scale - lrow[hh]);
-          s[nt][e] = pv * (dp[nt][e] - drow[hh]) * p.scale;  // dS
+          const float pv = ex2_approx_fwd(fmaf(s[nt][e], sl2, nl[hh]));
+          s[nt][e] = pv * fmaf(dp[nt][e], p.scale, -dsc[hh]);   // dS
         }
+      }
       mma_p_y(dq, s, sKb, lane);
     }
   }
@@ -567,6 +581,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnParams p) {
   const float* Dg = p.D + ((int64_t)b * p.H + h) * p.Sq;
   uint32_t kf[4][4], vf[4][4];
   const int r_lo = k0 + warp * 16 + g;  // key index of this thread's rows
+  const float sl2 = p.scale * 1.4426950408889634f;
   bool rpad[2];
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
@@ -583,15 +598,16 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnParams p) {
   for (int qq0 = qstart; qq0 < p.Sq; qq0 += SB) {
     __syncthreads();
     if (qq0 == qstart) {
-      load_tile_async(sKr, kg, p.ldk, k0, p.Sk, TK);
-      load_tile_async(sVr, vg, p.ldv, k0, p.Sk, TK);
+      load_rows_async(sKr, kg + (int64_t)k0 * p.ldk, p.ldk, p.Sk - k0, TK, threadIdx.x, 128);
+      load_rows_async(sVr, vg + (int64_t)k0 * p.ldv, p.ldv, p.Sk - k0, TK, threadIdx.x, 128);
     }
-    load_tile_async(sQ, qg, p.ldq, qq0, p.Sq, SB);
-    load_tile_async(sdO, dog, p.lddo, qq0, p.Sq, SB);
-    if (threadIdx.x < SB) {
+    load_rows_async(sQ, qg + (int64_t)qq0 * p.ldq, p.ldq, p.Sq - qq0, SB, threadIdx.x, 128);
+    load_rows_async(sdO, dog + (int64_t)qq0 * p.lddo, p.lddo, p.Sq - qq0, SB, threadIdx.x, 128);
+    if (threadIdx.x < SB) {   // per-query constants in the log2 domain: -lse*log2e (-inf for dead / absent rows), D*scale
       const int r = qq0 + threadIdx.x;
-      sL[threadIdx.x] = r < p.Sq ? lse[r] : -INFINITY;
-      sD[threadIdx.x] = r < p.Sq ? Dg[r] : 0.f;
+      const float l = r < p.Sq ? lse[r] : -INFINITY;
+      sL[threadIdx.x] = l == -INFINITY ? -INFINITY : -l * 1.4426950408889634f;
+      sD[threadIdx.x] = (r < p.Sq ? Dg[r] : 0.f) * p.scale;
     }
     cp_async_wait_all();
     __syncthreads();
@@ -615,18 +631,22 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnParams p) {
       mma_a_yt(dpt, vf, sdOb, lane);   // dP^T = V dO^T
       float ds[8][4];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 nl2 = *reinterpret_cast<const float2*>(sLb + nt * 8 + 2 * t);   // queries nt*8 + 2t, +1
+        const float2 dd2 = *reinterpret_cast<const float2*>(sDb + nt * 8 + 2 * t);
+        const bool diag = p.causal && k0 + warp * 16 + 15 > q0 + nt * 8;             // warp-uniform: tile touches the diagonal
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int cl = nt * 8 + 2 * t + (e & 1);  // query within block
           const int hh = e >> 1;
-          const int key = r_lo + hh * 8;
-          const float l = sLb[cl];
-          const bool masked = rpad[hh] || l == -INFINITY || (p.causal && key > (q0 + cl));
-          const float pv = masked ? 0.f : __expf(st[nt][e] * p.scale - l);
-          st[nt][e] = pv;                                        // P^T
-          ds[nt][e] = pv * (dpt[nt][e] - sDb[cl]) * p.scale;     // dS^T
+          const float nlq = (e & 1) ? nl2.y : nl2.x;
+          const float ddq = (e & 1) ? dd2.y : dd2.x;
+          bool masked = rpad[hh];
+          if (diag) masked = masked || (r_lo + hh * 8 > q0 + nt * 8 + 2 * t + (e & 1));
+          const float pv = masked ? 0.f : ex2_approx_fwd(fmaf(st[nt][e], sl2, nlq));
+          st[nt][e] = pv;                                              // P^T
+          ds[nt][e] = pv * fmaf(dpt[nt][e], p.scale, -ddq);            // dS^T
         }
+      }
       mma_p_y(dv, st, sdOb, lane);
       mma_p_y(dk, ds, sQb, lane);
     }
