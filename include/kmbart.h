@@ -282,6 +282,12 @@ int kmb_adamw_chunk_elems(void);
 int kmb_adamw_multi(const void* table_dev, const void* chunk_map_dev, int n_chunks, int* step_dev, double lr,
                     double beta1, double beta2, double eps, double weight_decay, int correct_bias,
                     const float* inv_scale_dev, kmb_stream_t stream);
+/* the same update over a sub-range of the chunk map; advance_step = 0 re-uses the step / step size of the
+ * preceding call of the same optimizer step (the data-parallel path updates the parameters whose gradient
+ * exchange has finished while the last all-reduce is still in flight, then the rest: kmbart/optim.py) */
+int kmb_adamw_multi_part(const void* table_dev, const void* chunk_map_dev, int n_chunks, int* step_dev, double lr,
+                         double beta1, double beta2, double eps, double weight_decay, int correct_bias,
+                         const float* inv_scale_dev, int advance_step, kmb_stream_t stream);
 int kmb_cast_bf16(const float* src, void* dst, int64_t n, kmb_stream_t stream);
 int kmb_repack_img_weight(const float* w, void* w_feat_bf16, float* w_box, int d, int fin, kmb_stream_t stream);
 /* attention_mask (int64, 1 = keep) -> padding bytes (1 = pad): HF-3.0.2 invert_mask

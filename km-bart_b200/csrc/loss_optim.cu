@@ -284,15 +284,15 @@ extern "C" int kmb_small_xent(const float* logits, int64_t ld, int n, int C, int
 
 extern "C" int kmb_adamw_chunk_elems(void) { return ADAM_CHUNK; }
 
-extern "C" int kmb_adamw_multi(const void* table_dev, const void* chunk_map_dev, int n_chunks, int* step_dev, double lr,
-                               double beta1, double beta2, double eps, double weight_decay, int correct_bias,
-                               const float* inv_scale_dev, kmb_stream_t stream) {
+extern "C" int kmb_adamw_multi_part(const void* table_dev, const void* chunk_map_dev, int n_chunks, int* step_dev, double lr,
+                                    double beta1, double beta2, double eps, double weight_decay, int correct_bias,
+                                    const float* inv_scale_dev, int advance_step, kmb_stream_t stream) {
   if (!table_dev || !chunk_map_dev || n_chunks <= 0 || !step_dev) {
     kmb_set_last_error("kmb_adamw_multi: bad argument", __FILE__, __LINE__);
     return KMB_ERR_ARG;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  step_incr_kernel<<<1, 1, 0, st>>>(step_dev, lr, beta1, beta2, correct_bias);
+  if (advance_step) step_incr_kernel<<<1, 1, 0, st>>>(step_dev, lr, beta1, beta2, correct_bias);
   AdamHyper h;
   h.lr = (float)lr; h.beta1 = (float)beta1; h.beta2 = (float)beta2; h.omb1 = (float)(1.0 - beta1); h.omb2 = (float)(1.0 - beta2);
   h.eps = (float)eps; h.weight_decay = (float)weight_decay; h.lr_wd = (float)(lr * weight_decay);
@@ -300,6 +300,13 @@ extern "C" int kmb_adamw_multi(const void* table_dev, const void* chunk_map_dev,
   launch_pdl(adamw_multi_kernel, dim3(n_chunks), dim3(256), 0, st, (const AdamTensor*)table_dev, (const int2*)chunk_map_dev, h);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
+}
+
+extern "C" int kmb_adamw_multi(const void* table_dev, const void* chunk_map_dev, int n_chunks, int* step_dev, double lr,
+                               double beta1, double beta2, double eps, double weight_decay, int correct_bias,
+                               const float* inv_scale_dev, kmb_stream_t stream) {
+  return kmb_adamw_multi_part(table_dev, chunk_map_dev, n_chunks, step_dev, lr, beta1, beta2, eps, weight_decay, correct_bias,
+                              inv_scale_dev, 1, stream);
 }
 
 extern "C" int kmb_cast_bf16(const float* src, void* dst, int64_t n, kmb_stream_t stream) {

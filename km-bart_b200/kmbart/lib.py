@@ -93,6 +93,8 @@ _PROTOS = {
     "kmb_adamw_chunk_elems": [],
     "kmb_adamw_multi": [c_void_p, c_void_p, c_int, c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_int,
                         c_void_p, c_void_p],
+    "kmb_adamw_multi_part": [c_void_p, c_void_p, c_int, c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_int,
+                             c_void_p, c_int, c_void_p],
     "kmb_cast_bf16": [c_void_p, c_void_p, c_int64, c_void_p],
     "kmb_repack_img_weight": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "kmb_invert_mask": [c_void_p, c_void_p, c_int64, c_void_p],

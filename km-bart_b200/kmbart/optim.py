@@ -40,12 +40,37 @@ class AdamW(torch.optim.Optimizer):
             return 0
         return store.P16.data_ptr() + off // 2
 
+    @staticmethod
+    def _reducer(p):
+        store = getattr(p, "_kmb_store", None)
+        return getattr(store, "grad_reducer", None) if store is not None else None
+
+    def _in_tail(self, p):
+        red = self._reducer(p)
+        if red is None or not getattr(red, "defer_tail", False):
+            return False
+        store = p._kmb_store
+        off = (p.data_ptr() - store.P.data_ptr()) // 4
+        return any(a <= off < b for a, b in red.tail_ranges)
+
+    def _ordered(self, group):
+        """Parameters with gradients; those whose gradient exchange may still be in flight when step() starts
+        (FlatGradReducer(defer_tail=True)) go last: step() launches the head, joins the exchange, then the tail."""
+        plist = [p for p in group["params"] if p.grad is not None]
+        tail = [self._in_tail(p) for p in plist]
+        if not any(tail):
+            return plist
+        return [p for p, t in zip(plist, tail) if not t] + [p for p, t in zip(plist, tail) if t]
+
     def _build_table(self, gi, group):
         lib = L.load()
         chunk = lib.kmb_adamw_chunk_elems()
-        plist = [p for p in group["params"] if p.grad is not None]
+        plist = self._ordered(group)
         rows, cmap = [], []
+        n_head_chunks = None
         for ti, p in enumerate(plist):
+            if n_head_chunks is None and self._in_tail(p):
+                n_head_chunks = len(cmap) // 2
             st = self.state[p]
             if len(st) == 0:
                 st["step"] = 0
@@ -65,13 +90,13 @@ class AdamW(torch.optim.Optimizer):
         step0 = max((self.state[p]["step"] for p in plist), default=0)
         step_dev = torch.tensor([step0, 0], dtype=torch.int32, device=dev)   # {step, float step_size}
         sig = tuple(rows)
-        return {"sig": sig, "table": table, "cmap": cm, "n_chunks": len(cmap) // 2, "step": step_dev, "plist": plist}
+        n_chunks = len(cmap) // 2
+        return {"sig": sig, "table": table, "cmap": cm, "n_chunks": n_chunks, "step": step_dev, "plist": plist,
+                "n_head": n_chunks if n_head_chunks is None else n_head_chunks}
 
     def _signature(self, group):
         sig = []
-        for p in group["params"]:
-            if p.grad is None:
-                continue
+        for p in self._ordered(group):
             st = self.state.get(p, {})
             ea, es = st.get("exp_avg"), st.get("exp_avg_sq")
             sig += [p.data_ptr(), p.grad.data_ptr(), ea.data_ptr() if ea is not None else 0,
@@ -95,11 +120,24 @@ class AdamW(torch.optim.Optimizer):
                 t = self._build_table(gi, group)
                 self._tables[gi] = t
             stream = torch.cuda.current_stream(t["table"].device).cuda_stream
-            L.check(lib.kmb_adamw_multi(t["table"].data_ptr(), t["cmap"].data_ptr(), t["n_chunks"], t["step"].data_ptr(),
-                                        float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]),
-                                        float(group["eps"]), float(group["weight_decay"]), int(bool(group["correct_bias"])),
-                                        0, stream), "kmb_adamw_multi")
-            self.launches_last += 2
+            hyper = (float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]),
+                     float(group["weight_decay"]), int(bool(group["correct_bias"])), 0)
+            reducers = {id(r): r for r in (self._reducer(p) for p in t["plist"]) if r is not None}
+            n_head, n_all = t["n_head"], t["n_chunks"]
+            if n_head in (0, n_all):        # nothing deferred (or everything): one launch
+                for r in reducers.values():
+                    r.wait_tail()
+                L.check(lib.kmb_adamw_multi(t["table"].data_ptr(), t["cmap"].data_ptr(), n_all, t["step"].data_ptr(), *hyper, stream),
+                        "kmb_adamw_multi")
+                self.launches_last += 2
+            else:                           # head while the last all-reduce is in flight, join, tail
+                L.check(lib.kmb_adamw_multi_part(t["table"].data_ptr(), t["cmap"].data_ptr(), n_head, t["step"].data_ptr(), *hyper, 1,
+                                                 stream), "kmb_adamw_multi_part")
+                for r in reducers.values():
+                    r.wait_tail()
+                L.check(lib.kmb_adamw_multi_part(t["table"].data_ptr(), t["cmap"].data_ptr() + 8 * n_head, n_all - n_head,
+                                                 t["step"].data_ptr(), *hyper, 0, stream), "kmb_adamw_multi_part")
+                self.launches_last += 3
             for p in t["plist"]:
                 self.state[p]["step"] += 1
                 store = getattr(p, "_kmb_store", None)

@@ -54,10 +54,17 @@ def plan_regions(names, offsets, numels, small_end, total, n_dec, n_enc):
 
 
 class FlatGradReducer:
-    def __init__(self, model, process_group=None, broadcast_parameters=True, engine=None):
+    def __init__(self, model, process_group=None, broadcast_parameters=True, engine=None, defer_tail=False):
         """`engine`: anything with `.store` (a kmbart.engine.ParamStore), `.cfg`, `.plans` — defaults to the model's
-        sm_100a engine; the CPU/gloo tests pass a stand-in that only owns a ParamStore."""
+        sm_100a engine; the CPU/gloo tests pass a stand-in that only owns a ParamStore.
+        `defer_tail=True`: finish() does not join the exchange of the LAST regions (tied embedding + small tensors:
+        their gradient is only final when the sweep ends, so this all-reduce can never overlap with backward);
+        `kmbart.optim.AdamW.step()` then updates every other parameter first and joins (`wait_tail()`) before it
+        touches the deferred ranges.  Anything else that reads `.grad` between backward and the optimizer step
+        (clipping, GradScaler.unscale_) must call `wait_tail()` itself — hence opt-in."""
         self.model = model
+        self.defer_tail = bool(defer_tail)
+        self.tail_pending = []
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         eng = engine if engine is not None else model._engine()
@@ -69,6 +76,8 @@ class FlatGradReducer:
         self.enabled = True
         self.pending = []
         self.bytes_reduced = 0
+        self.tail_ranges = [(a, b) for a, b, s_ in self.regions if s_ is None]   # element ranges of the flat buffers
+        st.grad_reducer = self
         eng.grad_reducer = self
         eng.plans = {k: ({kk: vv for kk, vv in v.items() if not kk.startswith("bwd")} if isinstance(v, dict) else v)
                      for k, v in eng.plans.items()}   # backward plans are rebuilt with the reduction points
@@ -93,14 +102,28 @@ class FlatGradReducer:
         return 0
 
     def finish(self):
+        n_before = len(self.pending)
         self.launch_stage(None)
-        for w in self.pending:
-            w.wait()
+        tail = self.pending[n_before:]
+        head = self.pending[:n_before]
         self.pending = []
+        for w in head:
+            w.wait()
+        if self.defer_tail and self.eng.store.G.is_cuda:
+            self.tail_pending = tail          # joined by AdamW.step() / wait_tail()
+        else:
+            for w in tail:
+                w.wait()
         if getattr(self, "_scale_cpu", False):   # gloo has no AVG
             self.eng.store.G.div_(self.world)
             self._scale_cpu = False
         return 0
+
+    def wait_tail(self):
+        """Orders the current stream after the deferred exchange of the last regions (no-op when nothing is pending)."""
+        for w in self.tail_pending:
+            w.wait()
+        self.tail_pending = []
 
     class _NoSync:
         def __init__(self, r):

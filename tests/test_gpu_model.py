@@ -670,3 +670,34 @@ def test_large_variant_slice_matches_oracle():
     assert worst <= 3e-2, worst
     opt.step()
     assert model(**cb)[0].item() < loss.item()
+
+
+def test_split_optimizer_step_with_deferred_tail_matches_single_launch(fwd_setup):
+    """FlatGradReducer(defer_tail=True) makes kmbart.optim.AdamW update the parameters outside the last exchange
+    regions first and the rest after `wait_tail()` (two kmb_adamw_multi_part launches sharing one step / step size).
+    Single process (world 1, nothing to exchange), identical gradients written into the flat gradient buffer:
+    weights after 3 steps must be bit-identical to the one-launch optimizer's."""
+    from kmbart.optim import AdamW
+    from kmbart.parallel import FlatGradReducer
+    ocfg, sd, batch, _ = fwd_setup
+    cb = to_cuda_batch(batch)
+    finals = []
+    for defer in (False, True):
+        model = make_model(ocfg, sd, train=True)
+        model._engine()
+        if defer:
+            red = FlatGradReducer(model, defer_tail=True)
+            assert red.tail_ranges and red.world == 1
+        opt = AdamW(model.parameters(), lr=1e-3)
+        model(**cb)[0].backward()                       # creates the .grad views of the flat buffer
+        g = torch.Generator(device="cuda").manual_seed(77)
+        for _ in range(3):
+            for p_ in model.parameters():               # deterministic gradients (the backward's atomics reorder fp32 sums)
+                p_.grad.copy_(torch.randn(p_.shape, device="cuda", generator=g) * 1e-2)
+            opt.step()
+        if defer:
+            t = opt._tables[0]
+            assert 0 < t["n_head"] < t["n_chunks"] and opt.launches_last == 3
+        finals.append([p_.detach().clone() for p_ in model.parameters()])
+    for a_, b_ in zip(*finals):
+        assert torch.equal(a_, b_)
