@@ -294,7 +294,7 @@ def run_ours(args):
                 "peak_source": peak_src + " burst (kernel timed alone, L2 flushed between launches)",
                 "step_mfu": None}
 
-    gen = bench_generation(model, cfg, dev, rank, world, dist, hbm, peak_src)
+    gen = None if args.train_only else bench_generation(model, cfg, dev, rank, world, dist, hbm, peak_src)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -305,7 +305,7 @@ def run_ours(args):
     e2e_value = samples / (ms_e2e * 1e-3)
     roof["step_mfu"] = round(value / world * FLOP_PER_SAMPLE / 1e12 / sustained, 4)
     roof["step_mfu_peak"] = f"{sustained} TFLOP/s ({peak_src} sustained)"
-    cpu = cpu_baseline(sample_steps=1)
+    cpu = None if args.train_only else cpu_baseline(sample_steps=1)
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
@@ -399,6 +399,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--train-only", action="store_true", help="experiments: skip the generation legs and the CPU baseline")
     ap.add_argument("--ddp", action="store_true", help="N > 1: wrap in torch DDP (reference scripts' way) instead of FlatGradReducer")
     args = ap.parse_args()
     if args.impl == "reference":
