@@ -163,7 +163,12 @@ __device__ __forceinline__ void store_rows(bf16* g, int64_t ld, int r_lo, int nr
 }
 
 // ------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
+// NW warps per CTA = 16 * NW query rows: the launcher picks NW = ceil(Sq / 16) when one CTA can own every query row
+// of a (batch, head) pair (Sq <= 128: K / V are then read once per pair and no warp idles on padding rows:
+// Sq = 100 -> 7 warps, Sq = 48 -> 3), else 4-warp tiles of 64 rows.
+template <int NW>
+__global__ void __launch_bounds__(32 * NW) attn_fwd_kernel(const AttnParams p) {
+  constexpr int TQ = 16 * NW;
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) uint8_t dsm[];
@@ -189,14 +194,14 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
   if (p.causal && q0 + TQ < kend) kend = q0 + TQ;
   for (int kk0 = 0; kk0 < kend; kk0 += SB) {
     __syncthreads();
-    if (kk0 == 0) load_rows_async(sQ, qg + (int64_t)q0 * p.ldq, p.ldq, p.Sq - q0, TQ, threadIdx.x, 128);
-    load_rows_async(sK, kg + (int64_t)kk0 * p.ldk, p.ldk, p.Sk - kk0, SB, threadIdx.x, 128);
-    load_rows_async(sV, vg + (int64_t)kk0 * p.ldv, p.ldv, p.Sk - kk0, SB, threadIdx.x, 128);
-    {
-      const int c = kk0 + threadIdx.x;   // 128 threads = the SB resident keys
+    if (kk0 == 0) load_rows_async(sQ, qg + (int64_t)q0 * p.ldq, p.ldq, p.Sq - q0, TQ, threadIdx.x, 32 * NW);
+    load_rows_async(sK, kg + (int64_t)kk0 * p.ldk, p.ldk, p.Sk - kk0, SB, threadIdx.x, 32 * NW);
+    load_rows_async(sV, vg + (int64_t)kk0 * p.ldv, p.ldv, p.Sk - kk0, SB, threadIdx.x, 32 * NW);
+    for (int w = warp; w < SB / 32; w += NW) {   // one ballot per 32 resident keys
+      const int c = kk0 + w * 32 + lane;
       const bool masked = c >= p.Sk || (p.key_pad && p.key_pad[(int64_t)b * p.Sk + c]);
       const uint32_t bits = __ballot_sync(0xffffffffu, masked);
-      if (lane == 0) sBits[warp] = bits;
+      if (lane == 0) sBits[w] = bits;
     }
     cp_async_wait_all();
     __syncthreads();
@@ -958,14 +963,22 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const Att
   }
 }
 
-constexpr int SMEM_FWD = (TQ + 2 * SB) * LDS * 2 + SB;
+constexpr int SMEM_FWD_MAX = (128 + 2 * SB) * LDS * 2 + SB;   // 8-warp instantiation
+constexpr int smem_fwd(int nw) { return (16 * nw + 2 * SB) * LDS * 2 + SB; }
 constexpr int SMEM_DQ = (2 * TQ + 2 * SB) * LDS * 2 + SB;
 constexpr int SMEM_DKV = (2 * TK + 2 * SB) * LDS * 2 + 2 * SB * 4;
 
 static int set_attn_smem_attrs() {
   static bool done = false;
   if (done) return KMB_OK;
-  cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD);
+  cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd(4));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd(1));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd(2));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd(3));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd(5));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd(6));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd(7));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd(8));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV);
   if (e != cudaSuccess) {
@@ -1005,6 +1018,22 @@ static int check_attn_args(const AttnParams& p) {
   if (!(p.scale > 0.f)) return KMB_ERR_ARG;   // the kernels track the maximum of the raw scores and fold the scale into the exponent
   if ((p.ldq % 8) || (p.ldk % 8) || (p.ldv % 8)) return KMB_ERR_ARG;
   return KMB_OK;
+}
+
+// tiled forward launch: one CTA of ceil(Sq/16) warps per (batch, head) when Sq <= 128, else 64-row tiles
+static void launch_attn_fwd_tiled(const AttnParams& p, cudaStream_t st) {
+  const int nw = p.Sq <= 128 ? (p.Sq + 15) / 16 : 4;
+  const dim3 grid((p.Sq + 16 * nw - 1) / (16 * nw), p.H, p.B);
+  switch (nw) {
+    case 1: launch_pdl(attn_fwd_kernel<1>, grid, dim3(32), (size_t)smem_fwd(1), st, p); break;
+    case 2: launch_pdl(attn_fwd_kernel<2>, grid, dim3(64), (size_t)smem_fwd(2), st, p); break;
+    case 3: launch_pdl(attn_fwd_kernel<3>, grid, dim3(96), (size_t)smem_fwd(3), st, p); break;
+    case 5: launch_pdl(attn_fwd_kernel<5>, grid, dim3(160), (size_t)smem_fwd(5), st, p); break;
+    case 6: launch_pdl(attn_fwd_kernel<6>, grid, dim3(192), (size_t)smem_fwd(6), st, p); break;
+    case 7: launch_pdl(attn_fwd_kernel<7>, grid, dim3(224), (size_t)smem_fwd(7), st, p); break;
+    case 8: launch_pdl(attn_fwd_kernel<8>, grid, dim3(256), (size_t)smem_fwd(8), st, p); break;
+    default: launch_pdl(attn_fwd_kernel<4>, grid, dim3(128), (size_t)smem_fwd(4), st, p); break;
+  }
 }
 
 }  // namespace kmb
@@ -1054,8 +1083,7 @@ extern "C" int kmb_attn_fwd(const void* q, const void* k, const void* v, int64_t
       return KMB_OK;
     }
   }
-  dim3 grid((Sq + TQ - 1) / TQ, H, B);
-  launch_pdl(attn_fwd_kernel, dim3(grid), dim3(128), SMEM_FWD, (cudaStream_t)stream, p);
+  launch_attn_fwd_tiled(p, (cudaStream_t)stream);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }
@@ -1076,9 +1104,8 @@ extern "C" int kmb_attn_fwd_strided(const void* q, const void* k, const void* v,
   bool bad = head_dim != DH || !o || check_attn_args(p);
   for (int i = 0; i < 12; ++i) bad = bad || (strides12[i] % 8);
   if (bad) { kmb_set_last_error("kmb_attn_fwd_strided: bad argument", __FILE__, __LINE__); return KMB_ERR_ARG; }
-  dim3 grid((Sq + TQ - 1) / TQ, H, B);
   if (set_attn_smem_attrs()) return KMB_ERR_CUDA;
-  launch_pdl(attn_fwd_kernel, dim3(grid), dim3(128), SMEM_FWD, (cudaStream_t)stream, p);
+  launch_attn_fwd_tiled(p, (cudaStream_t)stream);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }
