@@ -58,6 +58,20 @@ def _worker(rank, world, port, out):
         red.finish()
         assert torch.allclose(st.G, torch.full_like(st.G, (1 + world) / 2))
         assert red.bytes_reduced == 4 * st.total
+        red.bytes_reduced = 0
+        # defer_tail: on a CPU group nothing is left in flight (finish() still joins everything) and wait_tail() is a no-op;
+        # the deferred ranges are exactly the stage-None regions (small tensors + tied embedding)
+        red.defer_tail = True
+        st.G.fill_(float(2 * rank + 1))
+        for s in range(cfg.decoder_layers + cfg.encoder_layers):
+            red.launch_stage(s)
+        red.finish()
+        assert red.tail_pending == []
+        red.wait_tail()
+        assert torch.allclose(st.G, torch.full_like(st.G, float(world)))          # mean of 1, 3 -> 2 at world 2
+        assert red.tail_ranges == [(a, b) for a, b, s_ in red.regions if s_ is None] and len(red.tail_ranges) >= 1
+        assert any(a <= st.offsets["model.shared.weight"] < b for a, b in red.tail_ranges)
+        red.defer_tail = False
         # no_sync(): accumulation micro-steps leave local gradients untouched
         st.G.fill_(float(rank + 1))
         with red.no_sync():
