@@ -620,27 +620,32 @@ __global__ void __launch_bounds__(256) embed_bwd_scatter_kernel(const float* dem
 }
 
 // dpos[s + off, :] (+)= sum_b demb[b, s, :]
+// grid (S, nsplit): block (s, y) sums batch elements y, y + nsplit, ... of position s; with nsplit > 1 the partial sums are
+// combined with atomics onto the (pre-cleared / accumulating) gradient, so a 100-position launch is not limited to 100 CTAs
 __global__ void pos_grad_kernel(const float* demb, float* dpos, int B, int S, int d, int pos_offset, int accumulate) {
   pdl_trigger();
   pdl_wait();
-  const int s = blockIdx.x;
+  const int s = blockIdx.x, nsplit = gridDim.y;
   for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
     float4 acc = make_float4(0, 0, 0, 0);
-    for (int b = 0; b < B; ++b) {
+#pragma unroll 4
+    for (int b = blockIdx.y; b < B; b += nsplit) {
       const float4 v = *reinterpret_cast<const float4*>(demb + ((int64_t)b * S + s) * d + c);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    float4* dst = reinterpret_cast<float4*>(dpos + (int64_t)(s + pos_offset) * d + c);
-    if (accumulate) {
-      const float4 o = *dst;
-      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    float* dst = dpos + (int64_t)(s + pos_offset) * d + c;
+    if (nsplit > 1) {
+      atomicAdd(dst, acc.x); atomicAdd(dst + 1, acc.y); atomicAdd(dst + 2, acc.z); atomicAdd(dst + 3, acc.w);
+    } else {
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      if (accumulate) {
+        const float4 o = *d4;
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+      }
+      *d4 = acc;
     }
-    *dst = acc;
   }
 }
-
-// dW_img[:, 2048:2052] and the fp32 column sums for the box path:
-// dWbox[c, j] += sum_r dvis[r, c] * box[r, j]
 __global__ void box_wgrad_kernel(const bf16* dvis, const float* boxes, float* dw_img, int R, int d, int ld_w,
                                  int rows_per_block) {
   pdl_trigger();
@@ -650,6 +655,7 @@ __global__ void box_wgrad_kernel(const bf16* dvis, const float* boxes, float* dw
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(R, r0 + rows_per_block);
   float a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 8
   for (int r = r0; r < r1; ++r) {
     const float g = __bfloat162float(dvis[(int64_t)r * d + c]);
     const float4 bx = __ldg(reinterpret_cast<const float4*>(boxes + (int64_t)r * 4));
@@ -895,7 +901,9 @@ extern "C" int kmb_embed_bwd(const float* demb, const int64_t* ids, const int* s
   const int M = B * S;
   launch_pdl(embed_bwd_scatter_kernel, dim3((M * 32 + 255) / 256), dim3(256), 0, st, demb, ids, slot_idx, d_tok, (bf16*)dvis_bf16, M, d, pad_id, embed_scale);
   KMB_CHECK_LAUNCH();
-  launch_pdl(pos_grad_kernel, dim3(S), dim3(192), 0, st, demb, dpos, B, S, d, pos_offset, accumulate_pos);
+  // accumulating launches (the training backward: the gradient buffer was cleared at the start of the sweep) split the batch
+  const int nsplit = (accumulate_pos && B >= 16) ? 8 : 1;
+  launch_pdl(pos_grad_kernel, dim3(S, nsplit), dim3(192), 0, st, demb, dpos, B, S, d, pos_offset, accumulate_pos);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
 }
@@ -906,7 +914,7 @@ extern "C" int kmb_box_wgrad(const void* dvis_bf16, const float* boxes, float* d
     kmb_set_last_error("kmb_box_wgrad: bad argument", __FILE__, __LINE__);
     return KMB_ERR_ARG;
   }
-  const int rpb = 128;
+  const int rpb = 32;
   launch_pdl(box_wgrad_kernel, dim3(dim3((d + 127) / 128, (R + rpb - 1) / rpb)), dim3(128), 0, (cudaStream_t)stream, (const bf16*)dvis_bf16, boxes, dw_img, R, d, ld_w, rpb);
   KMB_CHECK_LAUNCH();
   return KMB_OK;
