@@ -614,7 +614,11 @@ __global__ void __launch_bounds__(256) embed_bwd_scatter_kernel(const float* dem
       *reinterpret_cast<uint2*>(dvis + (int64_t)slot * d + c) = pack4(v);
     } else if (tok != pad_id) {
       float* dst = d_tok + tok * d + c;
-      atomicAdd(dst, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        red_add_v4(dst, v);   // one 16-byte reduction instead of four scalar atomics
+      } else {
+        atomicAdd(dst, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w);
+      }
     }
   }
 }
