@@ -152,6 +152,61 @@ int kmb_greedy_select(const float* logits, int64_t ld, int rows, int V, int eos_
                       int ban_eos, int cur_len, int64_t* unfinished, int64_t* sent_len, int64_t* out_tokens,
                       int64_t out_ld, int64_t* ids_next, kmb_stream_t stream);
 /* ------------------------------------------------------------------------------
+ * Persistent decode step, cluster variant (opt-in, KMBART_DECODE_CLUSTER=1): the whole cached decoder forward of ONE generation step in one launch of 4-CTA clusters
+ * (csrc/decode_step.cu): embedding, L decoder layers (LayerNorm-on-load, q|k|v projection fused with self-attention,
+ * out-proj, cross-q projection fused with cross-attention, out-proj, fc1+GELU, fc2 — six grid-barrier-separated phases
+ * per layer, K split four ways inside a cluster and reduced through distributed shared memory) and the final
+ * LayerNorm; each CTA prefetches its weight slices through a shared-memory ring ahead of the barriers.
+ * replaces: one `self(**model_inputs)` iteration of HF-3.0.2 _generate_no_beam_search / _generate_beam_search reached
+ *   from src/model/mixins.py:336-382 — BartDecoder.forward(use_cache=True) with DecoderLayer / SelfAttention cached
+ *   branches (instantiated src/model/model.py:35), i.e. the 67 kernels of the launch-chain version of the same step.
+ * Buffers: y0 / y1 fp32 [rows, d] hold the pre-LayerNorm residual stream (ping-pong), stats fp32
+ * [1 + 3L, rows, NP, 2] the per-strip (sum, sum of squares) partials of every residual state (NP = d / strip width:
+ * 32 for d = 768 / 1024, 16 for d = 128); x_f32 / x_b16 [rows, d] receive the final decoder state (LM-head operand);
+ * ctx [rows, d] and h [rows, F] bf16 are scratch; barrier points at ONE 64-bit counter zeroed once per session and used
+ * by every launch of that session.  Layer caches are [rows, max_len, 3d] (q|k|v per position; the step writes k|v of
+ * position t); row j reads position p < t of the self cache from row slot_tbl[j * max_len + p] (beam ancestry, or NULL =
+ * own row); cross K/V are [n_samples * Se, 2d], sample = row / row_div; key_pad [n_samples, Se] bytes (1 = pad) or NULL.
+ * d in {128, 768, 1024}, head_dim 64, max_len and Se <= 512.
+ */
+#define KMB_DECODE_MAX_LAYERS 12
+#define KMB_DECODE_NO_CROSS_PREFETCH 1
+#define KMB_DECODE_NO_SELF_PREFETCH 2
+typedef struct KmbDecodeLayer {
+  const void *w_qkv, *w_o, *w_cq, *w_co, *w_fc1, *w_fc2;      /* bf16 [3d,d] [d,d] [d,d] [d,d] [F,d] [d,F] */
+  const float *b_qkv, *b_o, *b_cq, *b_co, *b_fc1, *b_fc2;
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b; /* self_attn / encoder_attn / final layer norms */
+  void* cache;                                                /* bf16 [rows, max_len, 3d] */
+  const void* cross_kv;                                       /* bf16 [n_samples * Se, 2d] */
+  const void* packed[6];                                      /* kmb_decode_pack_weights images of w_qkv, w_o, w_cq, w_co, w_fc1, w_fc2 */
+} KmbDecodeLayer;
+typedef struct KmbDecodeStepC {
+  int32_t rows, d, H, F, L, t, max_len, Se, row_div, pos_row; /* pos_row = t + position offset (2) */
+  float embed_scale, attn_scale;
+  int32_t flags, reserved;                                    /* tuning switches (KMB_DECODE_*), 0 = defaults */
+  const int64_t* ids;                                         /* [rows] token fed to this step */
+  const float *tok_emb, *pos_emb, *lne_g, *lne_b;             /* fp32 [V,d], [npos,d], layernorm_embedding */
+  const int32_t* slot_tbl;
+  const uint8_t* key_pad;
+  float *y0, *y1, *stats;
+  float* x_f32; void* x_b16; void* ctx; void* h;
+  unsigned long long* barrier;
+  unsigned long long* trace;   /* NULL, or [n_barriers][grid][2] globaltimer ns: {arrive, release} of every grid barrier (profiling aid) */
+  KmbDecodeLayer layers[KMB_DECODE_MAX_LAYERS];
+} KmbDecodeStepC;
+int kmb_decode_step_cluster(const KmbDecodeStepC* step, kmb_stream_t stream);
+/* Weight images for the step's shared-memory ring: every (column strip, K quarter, K chunk) slice of a weight matrix
+ * stored contiguously with the ring's row pitch, so a ring slot is filled by ONE bulk copy.  Pack once per weight
+ * version; kmb_decode_pack_offsets gives the byte offsets of the six sections inside one layer's image (off7[6] = bytes
+ * per layer), kmb_decode_pack_weights fills one layer's image from layer->w_*. */
+int kmb_decode_pack_offsets(int d, int H, int F, int64_t* off7);
+int kmb_decode_pack_weights(const KmbDecodeLayer* layer, int d, int H, int F, void* out, kmb_stream_t stream);
+/* CTAs of the persistent grid for model width d (4 x the number of co-resident clusters, at most 128) */
+int kmb_decode_cluster_grid(int d);
+/* grid barriers of one step (first dimension of the trace buffer) */
+int kmb_decode_cluster_barriers(int n_layers);
+
+/* ------------------------------------------------------------------------------
  * Persistent decode step: the whole cached decoder forward of ONE generation step in one cooperative launch
  * (embedding + LayerNorm, L decoder layers with self / cross attention over the preallocated caches, FFN), grid-wide
  * barriers between the dependent sub-steps and a shared-memory weight ring that prefetches each CTA's weight slices
@@ -166,14 +221,6 @@ int kmb_greedy_select(const float* logits, int64_t ld, int rows, int V, int eos_
  * cache from row slot_tbl[j * max_len + p] (beam ancestry, or NULL = own row); cross K/V are [n_samples * Se, 2d],
  * sample = row / row_div; key_pad [n_samples, Se] bytes (1 = pad) or NULL.  d = 768, head_dim 64, max_len and Se <= 512.
  */
-#define KMB_DECODE_MAX_LAYERS 12
-typedef struct KmbDecodeLayer {
-  const void *w_qkv, *w_o, *w_cq, *w_co, *w_fc1, *w_fc2;      /* bf16 [3d,d] [d,d] [d,d] [d,d] [F,d] [d,F] */
-  const float *b_qkv, *b_o, *b_cq, *b_co, *b_fc1, *b_fc2;
-  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b; /* self_attn / encoder_attn / final layer norms */
-  void* cache;                                                /* bf16 [rows, max_len, 3d] */
-  const void* cross_kv;                                       /* bf16 [n_samples * Se, 2d] */
-} KmbDecodeLayer;
 typedef struct KmbDecodeStep {
   int32_t rows, d, H, F, L, t, max_len, Se, row_div, pos_row; /* pos_row = t + position offset (2) */
   float embed_scale, attn_scale;
@@ -184,6 +231,7 @@ typedef struct KmbDecodeStep {
   const uint8_t* key_pad;
   float* x_f32; void* x_b16; void* ctx; float* lin; void* q2; void* h;
   unsigned long long* barrier;
+  unsigned long long* trace;   /* NULL, or [n_barriers][grid][2] globaltimer ns: {arrive, release} of every grid barrier (profiling aid) */
   KmbDecodeLayer layers[KMB_DECODE_MAX_LAYERS];
 } KmbDecodeStep;
 int kmb_decode_step(const KmbDecodeStep* step, kmb_stream_t stream);

@@ -89,11 +89,20 @@ __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 
 // Monotonic 64-bit arrival counter shared by every launch of a session (never reset): a launch starts from the
 // largest multiple of gridDim.x not above the value it first observes (a late CTA can see at most gridDim.x - 1
 // early arrivals of barrier 0).  Bounded spin: a scheduling accident traps instead of hanging the box.
+__device__ __forceinline__ unsigned long long mg_gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 struct GridBar {
   unsigned long long* ctr;
   unsigned long long target;
-  __device__ void init(unsigned long long* c) {
+  unsigned long long* trace;   // optional {arrive, release} timestamps per barrier and CTA
+  int n;
+  __device__ void init(unsigned long long* c, unsigned long long* tr) {
     ctr = c;
+    trace = tr;
+    n = 0;
     const unsigned long long v = ld_acquire_u64(c);
     target = v - v % gridDim.x;
   }
@@ -101,6 +110,7 @@ struct GridBar {
     __syncthreads();
     target += gridDim.x;
     if (threadIdx.x == 0) {
+      if (trace) trace[((size_t)n * gridDim.x + blockIdx.x) * 2] = mg_gtimer();
       __threadfence();
       atomicAdd(ctr, 1ULL);
       const long long t0 = clock64();
@@ -110,7 +120,9 @@ struct GridBar {
           __trap();
         }
       }
+      if (trace) trace[((size_t)n * gridDim.x + blockIdx.x) * 2 + 1] = mg_gtimer();
     }
+    ++n;
     __syncthreads();
   }
 };
@@ -505,7 +517,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const __grid
   if (threadIdx.x < 32)
     for (int i = 0; i < C::NSLOT; ++i) ring_advance<D>(p, ring);   // the weight stream starts before anything else
   GridBar bar;
-  bar.init(p.barrier);
+  bar.init(p.barrier, p.trace);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* xf = p.x_f32;

@@ -28,6 +28,30 @@ from . import lib as L
 from .engine import Plan, BF16, F32, _ptr
 
 
+def packed_decoder_weights(eng):
+    """Ring-slot images of the decoder weights (kmb_decode_pack_weights), rebuilt when the bf16 shadow changes.
+    Returns (buffer, bytes per layer, section offsets)."""
+    cfg, d, st = eng.cfg, eng.cfg.d_model, eng.store
+    cached = getattr(eng, "_decode_packed", None)
+    if cached is not None and cached[0] == st.shadow_version:
+        return cached[1:]
+    H, F_, Ld = cfg.decoder_attention_heads, cfg.decoder_ffn_dim, cfg.decoder_layers
+    off = (ctypes.c_int64 * 7)()
+    L.check(eng.lib.kmb_decode_pack_offsets(d, H, F_, off), "kmb_decode_pack_offsets")
+    per_layer = int(off[6])
+    buf = cached[1] if cached is not None else torch.empty(Ld * per_layer, dtype=torch.uint8, device=eng.device)
+    for l in range(Ld):
+        lp, y = eng.n(f"decoder.layers.{l}"), L.DecodeLayer()
+        y.w_qkv = _ptr(st.p16(lp + ".self_attn.q_proj.weight", 3 * d))
+        for key, name in (("o", "self_attn.out_proj"), ("cq", "encoder_attn.q_proj"), ("co", "encoder_attn.out_proj"),
+                          ("fc1", "fc1"), ("fc2", "fc2")):
+            setattr(y, "w_" + key, _ptr(st.p16(f"{lp}.{name}.weight")))
+        L.check(eng.lib.kmb_decode_pack_weights(ctypes.byref(y), d, H, F_, buf.data_ptr() + l * per_layer, eng.stream()),
+                "kmb_decode_pack_weights")
+    eng._decode_packed = (st.shadow_version, buf, per_layer, [int(o) for o in off])
+    return eng._decode_packed[1:]
+
+
 class DecodeSession:
     def __init__(self, eng, B, Se, rows, max_len, has_pad):
         cfg, dev, d = eng.cfg, eng.device, eng.cfg.d_model
@@ -53,9 +77,16 @@ class DecodeSession:
         # persistent single-launch step (csrc/decode_mega.cu); KMBART_DECODE_CHAIN=1 keeps the per-op launch chain
         self.mega = (d in (128, 768, 1024) and cfg.decoder_attention_heads * 64 == d and F_ % d == 0 and max_len <= 512 and Se <= 512
                      and Ld <= L.DECODE_MAX_LAYERS and os.environ.get("KMBART_DECODE_CHAIN", "0") != "1")
+        # KMBART_DECODE_CLUSTER=1: the 4-CTA-cluster variant of the persistent step (csrc/decode_cluster.cu, 6 phases per layer,
+        # K split inside a cluster, LayerNorm on load); correct and bit-reproducible but not faster yet (profiles/r02_decode_analysis.md)
+        self.cluster = self.mega and os.environ.get("KMBART_DECODE_CLUSTER", "0") == "1"
         if self.mega:
             self.lin_f32 = torch.zeros(rows, d, dtype=F32, device=dev)
             self.grid_barrier = torch.zeros(2, dtype=torch.int64, device=dev)
+        if self.cluster:   # fp32 pre-LayerNorm residual stream (ping-pong) + per-strip row statistics
+            self.np_stats = d // (24 if d == 768 else 32 if d == 1024 else 8)
+            self.y_pre = [torch.zeros(rows, d, dtype=F32, device=dev) for _ in range(2)]
+            self.ln_stats = torch.zeros(1 + 3 * Ld, rows, self.np_stats, 2, dtype=F32, device=dev)
         self.use_tbl = False
         # greedy / sampling bookkeeping (device resident)
         self.out = torch.zeros(rows, max_len, dtype=torch.int64, device=dev)
@@ -78,6 +109,8 @@ class DecodeSession:
             eng.gemm(plan, self.enc_b16, st.p16(lp + ".encoder_attn.k_proj.weight", 2 * d), self.B * self.Se, 2 * d, d, d, d,
                      bias=st.fused32(lp + ".encoder_attn.k_proj.bias", 2), out_bf16=self.kv2[l])
         plan.run()
+        if self.cluster:
+            packed_decoder_weights(eng)    # re-pack (in place: captured graphs stay valid) when the weights changed
         self.use_tbl = use_tbl
         if use_tbl:
             self.slot_tbl.copy_(self.rows_i32.expand(self.rows, self.max_len))
@@ -89,10 +122,10 @@ class DecodeSession:
 
     # ------------------------------------------------------------------ the kernel chain of step t
     def _mega_args(self, t):
-        """struct KmbDecodeStep of step t (include/kmbart.h)."""
+        """struct KmbDecodeStep / KmbDecodeStepC of step t (include/kmbart.h)."""
         eng, cfg, d = self.eng, self.eng.cfg, self.eng.cfg.d_model
         st = eng.store
-        a = L.DecodeStep()
+        a = L.DecodeStepC() if self.cluster else L.DecodeStep()
         a.rows, a.d, a.H, a.F, a.L, a.t = self.rows, d, cfg.decoder_attention_heads, cfg.decoder_ffn_dim, cfg.decoder_layers, t
         a.max_len, a.Se, a.row_div, a.pos_row = self.max_len, self.Se, self.row_div, cfg.extra_pos_embeddings + t
         a.embed_scale = math.sqrt(d) if cfg.scale_embedding else 1.0
@@ -104,10 +137,19 @@ class DecodeSession:
         a.lne_b = _ptr(st.p32(eng.n("decoder.layernorm_embedding.bias")))
         a.slot_tbl = _ptr(self.slot_tbl) if self.use_tbl else 0
         a.key_pad = _ptr(self.pad_u8) if self.has_pad else 0
-        a.x_f32, a.x_b16, a.ctx, a.lin = _ptr(self.x_f32[0]), _ptr(self.x_b16[0]), _ptr(self.ctx), _ptr(self.lin_f32)
-        a.q2, a.h, a.barrier = _ptr(self.q2), _ptr(self.h), _ptr(self.grid_barrier)
+        a.x_f32, a.x_b16, a.ctx, a.h = _ptr(self.x_f32[0]), _ptr(self.x_b16[0]), _ptr(self.ctx), _ptr(self.h)
+        a.barrier = _ptr(self.grid_barrier)
+        if self.cluster:
+            a.flags = int(os.environ.get("KMBART_DECODE_FLAGS", "3"))   # L2 prefetches off: no gain measured (profiles/r02g)
+            a.y0, a.y1, a.stats = _ptr(self.y_pre[0]), _ptr(self.y_pre[1]), _ptr(self.ln_stats)
+            packed, per_layer, off = packed_decoder_weights(eng)
+        else:
+            a.lin, a.q2 = _ptr(self.lin_f32), _ptr(self.q2)
         for l in range(cfg.decoder_layers):
             lp, y = eng.n(f"decoder.layers.{l}"), a.layers[l]
+            if self.cluster:
+                for k in range(6):
+                    y.packed[k] = packed.data_ptr() + l * per_layer + off[k]
             y.w_qkv = _ptr(st.p16(lp + ".self_attn.q_proj.weight", 3 * d))
             y.b_qkv = _ptr(st.fused32(lp + ".self_attn.q_proj.bias", 3))
             for key, name in (("o", "self_attn.out_proj"), ("cq", "encoder_attn.q_proj"), ("co", "encoder_attn.out_proj"),
@@ -126,7 +168,7 @@ class DecodeSession:
         V = cfg.vocab_size
         if self.mega:
             args = self._mega_args(t)
-            plan.add(lib.kmb_decode_step, ctypes.byref(args), plan.stream, keep=args)
+            plan.add(lib.kmb_decode_step_cluster if self.cluster else lib.kmb_decode_step, ctypes.byref(args), plan.stream, keep=args)
             # LM head at M <= 128 is a pure weight stream (77 MB): narrow single-CTA tiles cut the wave-quantisation
             # loss of 197 tiles of 256 columns on 148 SMs (2 waves, the second a third full)
             eng.gemm(plan, self.x_b16[0], st.p16(eng.n("shared.weight")), rows, V, d, d, d, bias=self.flb, out_f32=self.logits, ld_f32=V,
@@ -186,7 +228,8 @@ class DecodeSession:
             logits[:, sel["eos"]] = -float("inf")
         if sel["do_sample"]:
             scores = logits / sel["temperature"] if sel["temperature"] != 1.0 else logits
-            k = min(max(sel["top_k"], 1), logits.shape[-1])
+            # HF-3.0.2 top_k_top_p_filtering: top_k == 0 means "no top-k filter" (sample over the whole vocabulary)
+            k = min(sel["top_k"], logits.shape[-1]) if sel["top_k"] > 0 else logits.shape[-1]
             vals, idx = torch.topk(scores, k, dim=-1)       # top-k filter + softmax == softmax over the k survivors
             probs = torch.softmax(vals, dim=-1)
             pick = torch.multinomial(probs, num_samples=1)

@@ -37,15 +37,24 @@ class DecodeLayer(C.Structure):
     """Mirror of struct KmbDecodeLayer."""
     _fields_ = [(n, c_void_p) for n in (
         "w_qkv", "w_o", "w_cq", "w_co", "w_fc1", "w_fc2", "b_qkv", "b_o", "b_cq", "b_co", "b_fc1", "b_fc2",
-        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "ln3_g", "ln3_b", "cache", "cross_kv")]
+        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "ln3_g", "ln3_b", "cache", "cross_kv")] + [("packed", c_void_p * 6)]
 
 
 class DecodeStep(C.Structure):
-    """Mirror of struct KmbDecodeStep."""
+    """Mirror of struct KmbDecodeStep (persistent decode step, csrc/decode_mega.cu)."""
     _fields_ = ([(n, C.c_int32) for n in ("rows", "d", "H", "F", "L", "t", "max_len", "Se", "row_div", "pos_row")]
                 + [("embed_scale", c_float), ("attn_scale", c_float), ("nt", C.c_int32 * 6)]
                 + [(n, c_void_p) for n in ("ids", "tok_emb", "pos_emb", "lne_g", "lne_b", "slot_tbl", "key_pad",
-                                           "x_f32", "x_b16", "ctx", "lin", "q2", "h", "barrier")]
+                                           "x_f32", "x_b16", "ctx", "lin", "q2", "h", "barrier", "trace")]
+                + [("layers", DecodeLayer * DECODE_MAX_LAYERS)])
+
+
+class DecodeStepC(C.Structure):
+    """Mirror of struct KmbDecodeStepC (cluster variant of the persistent decode step, csrc/decode_cluster.cu)."""
+    _fields_ = ([(n, C.c_int32) for n in ("rows", "d", "H", "F", "L", "t", "max_len", "Se", "row_div", "pos_row")]
+                + [("embed_scale", c_float), ("attn_scale", c_float), ("flags", C.c_int32), ("reserved", C.c_int32)]
+                + [(n, c_void_p) for n in ("ids", "tok_emb", "pos_emb", "lne_g", "lne_b", "slot_tbl", "key_pad",
+                                           "y0", "y1", "stats", "x_f32", "x_b16", "ctx", "h", "barrier", "trace")]
                 + [("layers", DecodeLayer * DECODE_MAX_LAYERS)])
 
 
@@ -68,6 +77,11 @@ _PROTOS = {
                      c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
     "kmb_decode_step": [C.POINTER(DecodeStep), c_void_p],
     "kmb_decode_step_grid": [],
+    "kmb_decode_step_cluster": [C.POINTER(DecodeStepC), c_void_p],
+    "kmb_decode_cluster_grid": [c_int],
+    "kmb_decode_cluster_barriers": [c_int],
+    "kmb_decode_pack_offsets": [c_int, c_int, c_int, C.POINTER(c_int64)],
+    "kmb_decode_pack_weights": [C.POINTER(DecodeLayer), c_int, c_int, c_int, c_void_p, c_void_p],
     "kmb_greedy_select": [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                           c_void_p, c_void_p],
     "kmb_attn_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,

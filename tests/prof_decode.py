@@ -5,7 +5,7 @@ import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "km-bart_b200"))
 import torch
-import bench
+from kmbart.synth import synthetic_batch, to_device
 from src.model.config import MultiModalBartConfig
 from src.model.model import MultiModalBartForConditionalGeneration
 
@@ -13,7 +13,7 @@ beam = len(sys.argv) > 1 and sys.argv[1] == "beam"
 cfg = MultiModalBartConfig.from_dict(json.load(open(os.path.join(ROOT, "configs", "vcg_base.json"))))
 torch.manual_seed(0)
 model = MultiModalBartForConditionalGeneration(cfg).cuda().eval()
-b = bench.make_batch(cfg, 4321, device="cuda", batch=64)
+b = to_device(synthetic_batch(cfg, batch=64, seed=4321), "cuda")
 gi = dict(input_ids=b["input_ids"], image_features=b["image_features"], attention_mask=b["attention_mask"])
 kw = dict(max_length=25, min_length=24, num_beams=5, early_stopping=True) if beam else dict(max_length=25, min_length=25)
 with torch.no_grad():

@@ -512,24 +512,27 @@ def test_fp32_mode_no_cache_decode_and_training_guard(golden, fwd_setup):
 
 
 # ------------------------------------------------------------------ persistent decode step (csrc/decode_mega.cu)
-def _decode_sessions(model, B, Se, rows, max_len, has_pad):
-    """One DecodeSession per implementation of the step: the single cooperative launch and the per-op launch chain."""
+def _decode_sessions(model, B, Se, rows, max_len, has_pad, cluster=False):
+    """One DecodeSession per implementation of the step: the single persistent launch (csrc/decode_mega.cu, or its
+    4-CTA-cluster variant csrc/decode_cluster.cu) and the per-op launch chain."""
     from kmbart.decode import DecodeSession
     eng = model._engine()
     eng.sync_shadow()
     out = []
     for chain in ("0", "1"):
         os.environ["KMBART_DECODE_CHAIN"] = chain
+        os.environ["KMBART_DECODE_CLUSTER"] = "1" if cluster else "0"
         try:
             out.append(DecodeSession(eng, B, Se, rows, max_len, has_pad))
         finally:
             os.environ.pop("KMBART_DECODE_CHAIN", None)
-    assert out[0].mega and not out[1].mega
+            os.environ.pop("KMBART_DECODE_CLUSTER", None)
+    assert out[0].mega and not out[1].mega and out[0].cluster == cluster
     return eng, out
 
 
-@pytest.mark.parametrize("rows_per_sample,has_pad", [(1, False), (5, True)])
-def test_persistent_decode_step_matches_launch_chain_base_size(rows_per_sample, has_pad):
+@pytest.mark.parametrize("rows_per_sample,has_pad,cluster", [(1, False, False), (5, True, False), (1, False, True), (5, True, True)])
+def test_persistent_decode_step_matches_launch_chain_base_size(rows_per_sample, has_pad, cluster):
     """Base model (d = 768, 6 decoder layers), S_e = 100: the logits of steps 0..5 from the one-launch persistent kernel
     agree with the 68-kernel chain (both bf16 operands / fp32 accumulation; the chain rounds Linear outputs to bf16
     before the LayerNorm, the persistent kernel keeps them fp32) — including beam ancestry re-ordering and key padding."""
@@ -548,7 +551,7 @@ def test_persistent_decode_step_matches_launch_chain_base_size(rows_per_sample, 
                 p.add_(0.1 * torch.randn(p.shape, generator=g, device="cuda"))
     B, Se, max_len = 7, 100, 12
     rows = B * rows_per_sample
-    eng, (mega, chain) = _decode_sessions(model, B, Se, rows, max_len, has_pad)
+    eng, (mega, chain) = _decode_sessions(model, B, Se, rows, max_len, has_pad, cluster)
     gen = torch.Generator(device="cuda").manual_seed(11)
     enc = torch.randn(B, Se, cfg.d_model, generator=gen, device="cuda")
     mask = torch.ones(B, Se, dtype=torch.long, device="cuda")
@@ -577,17 +580,21 @@ def test_persistent_decode_step_matches_launch_chain_base_size(rows_per_sample, 
     assert mega.launches_per_step <= 3 < chain.launches_per_step
 
 
-def test_persistent_decode_step_small_model_vs_oracle(fwd_setup):
-    """Small golden model (d = 128): greedy generation through the persistent step stays within the bf16 near-tie
-    band of the oracle, and the persistent step is the path generate() takes by default."""
+@pytest.mark.parametrize("cluster", [False, True])
+def test_persistent_decode_step_small_model_vs_oracle(fwd_setup, cluster, monkeypatch):
+    """Small golden model (d = 128): greedy generation through the persistent step (both variants) stays within the bf16
+    near-tie band of the oracle, and the persistent step is the path generate() takes by default."""
     ocfg, sd, batch, _ = fwd_setup
+    monkeypatch.setenv("KMBART_DECODE_CLUSTER", "1" if cluster else "0")
     model = make_model(ocfg, sd)
     cb = to_cuda_batch(batch)
     gi = dict(input_ids=cb["input_ids"], image_features=cb["image_features"], attention_mask=cb["attention_mask"])
     toks = model.generate(**gi, max_length=12)
+    toks2 = model.generate(**gi, max_length=12)
+    assert torch.equal(toks, toks2)
     eng = model._engine()
     sessions = [s for k, s in eng.arenas.items() if isinstance(k, tuple) and k and k[0] == "dec"]
-    assert sessions and all(s.mega for s in sessions)
+    assert sessions and all(s.mega and s.cluster == cluster for s in sessions)
     assert _near_tie_ok(sd, ocfg, batch, toks, 2e-2)
 
 
