@@ -151,6 +151,38 @@ int kmb_attn_f32(const float* q, int64_t q_row_stride, const float* k, const flo
 int kmb_greedy_select(const float* logits, int64_t ld, int rows, int V, int eos_token_id, int pad_token_id,
                       int ban_eos, int cur_len, int64_t* unfinished, int64_t* sent_len, int64_t* out_tokens,
                       int64_t out_ld, int64_t* ids_next, kmb_stream_t stream);
+/* Top-k sampling step of the no-beam loop, on device: temperature, top-k filter (0 = none; ties with the k-th value
+ * survive), softmax, one multinomial draw per row from hash(seed[0], row, cur_len), then the same bookkeeping as
+ * kmb_greedy_select.  One CTA per row holds the logits row in shared memory (V <= kmb_select_max_vocab()).
+ * replaces: HF-3.0.2 _generate_no_beam_search do_sample branch (top_k_top_p_filtering + softmax + multinomial) reached
+ *   from src/model/mixins.py:368-382 with the vcg_generate.py defaults (src/generation.py:22-32). */
+int kmb_select_max_vocab(void);
+int kmb_sample_select(const float* logits, int64_t ld, int rows, int V, float temperature, int top_k, int eos_token_id,
+                      int pad_token_id, int ban_eos, int cur_len, const uint64_t* seed, int64_t* unfinished,
+                      int64_t* sent_len, int64_t* out_tokens, int64_t out_ld, int64_t* ids_next, kmb_stream_t stream);
+/* Beam-search step on device (num_beams > 1, do_sample = False): log_softmax of the (optionally forced) logits, EOS ban
+ * below min_length, + beam_scores, top 2 * num_beams over beams x vocab per batch element, then the HF-3.0.2 candidate
+ * loop: EOS candidates ranked < num_beams become finished hypotheses (BeamHypotheses.add with length_penalty, worst-score
+ * eviction), the first num_beams others become the next beams, is_done / early_stopping; beams are re-ordered by
+ * permuting the token history and the cache ancestry table (slot_tbl, may be NULL), never the cache.
+ * replaces: the body of HF-3.0.2 _generate_beam_search reached from src/model/mixins.py:336-366, including
+ *   adjust_logits_during_generation / _force_token_ids_generation (src/model/mixins.py:400-417: force_token >= 0) and
+ *   _reorder_cache (src/model/mixins.py:419-434).  Hypotheses are read back and finalised on the host once, at the end.
+ * State (all device memory, rows = batch * num_beams): cand_* [rows, K] scratch; beam_scores [rows]; hist [rows, max_len]
+ * int32 tokens so far (column 0 = decoder start); ids_next [rows] int64 token fed to the next model step; beam_idx [rows]
+ * the parent row of every new beam (for callers that re-order a legacy cache); done / hyp_n [batch]; hyp_score
+ * [batch, num_beams + 1] double; hyp_len [batch, num_beams + 1]; hyp_tok [batch, num_beams + 1, max_len]; worst [batch]
+ * double (initialised to 1e9); done_count [1]. */
+typedef struct KmbBeamState {
+  int32_t batch, num_beams, K, V, eos, pad, max_len, early_stopping;
+  double length_penalty;
+  float* cand_val; int32_t* cand_tok;
+  float* beam_scores; int32_t* hist; int32_t* slot_tbl; int64_t* ids_next; int32_t* beam_idx;
+  int32_t* done; int32_t* hyp_n; double* hyp_score; int32_t* hyp_len; int32_t* hyp_tok; double* worst; int32_t* done_count;
+} KmbBeamState;
+int kmb_beam_step(const float* logits, int64_t ld, const KmbBeamState* state, int cur_len, int force_token, int ban_eos,
+                  kmb_stream_t stream);
+
 /* ------------------------------------------------------------------------------
  * Persistent decode step, cluster variant (opt-in, KMBART_DECODE_CLUSTER=1): the whole cached decoder forward of ONE generation step in one launch of 4-CTA clusters
  * (csrc/decode_step.cu): embedding, L decoder layers (LayerNorm-on-load, q|k|v projection fused with self-attention,

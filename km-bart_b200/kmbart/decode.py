@@ -52,6 +52,96 @@ def packed_decoder_weights(eng):
     return eng._decode_packed[1:]
 
 
+class BeamController:
+    """Device-resident beam-search state + the two-kernel step (kmb_beam_step, csrc/decode_control.cu): the body of
+    HF-3.0.2 _generate_beam_search (reached from src/model/mixins.py:336-366) without a host round trip per token.
+    Finished hypotheses stay on the device; finalize() reads them back once and runs the reference's selection /
+    padding epilogue on the host."""
+
+    def __init__(self, dev, batch, num_beams, V, max_len, eos, pad, early_stopping, length_penalty, slot_tbl=None, ids_next=None):
+        rows, K = batch * num_beams, 2 * num_beams
+        self.dev, self.batch, self.num_beams, self.V, self.max_len, self.rows = dev, batch, num_beams, V, max_len, rows
+        self.eos, self.pad, self.early_stopping, self.length_penalty = eos, pad, bool(early_stopping), float(length_penalty)
+        i32, f32, f64 = torch.int32, torch.float32, torch.float64
+        self.cand_val = torch.empty(rows, K, dtype=f32, device=dev)
+        self.cand_tok = torch.empty(rows, K, dtype=i32, device=dev)
+        self.beam_scores = torch.zeros(rows, dtype=f32, device=dev)
+        self.hist = torch.zeros(rows, max_len, dtype=i32, device=dev)
+        self.ids_next = ids_next if ids_next is not None else torch.zeros(rows, dtype=torch.int64, device=dev)
+        self.beam_idx = torch.zeros(rows, dtype=i32, device=dev)
+        self.done = torch.zeros(batch, dtype=i32, device=dev)
+        self.hyp_n = torch.zeros(batch, dtype=i32, device=dev)
+        self.hyp_score = torch.zeros(batch, num_beams + 1, dtype=f64, device=dev)
+        self.hyp_len = torch.zeros(batch, num_beams + 1, dtype=i32, device=dev)
+        self.hyp_tok = torch.zeros(batch, num_beams + 1, max_len, dtype=i32, device=dev)
+        self.worst = torch.zeros(batch, dtype=f64, device=dev)
+        self.done_count = torch.zeros(1, dtype=i32, device=dev)
+        self.init_scores = torch.zeros(batch, num_beams, dtype=f32, device=dev)
+        self.init_scores[:, 1:] = -1e9          # HF: beam_scores[:, 1:] = -1e9 when do_sample is False
+        st = L.BeamState()
+        st.batch, st.num_beams, st.K, st.V, st.max_len = batch, num_beams, K, V, max_len
+        st.eos = -1 if eos is None else int(eos)
+        st.pad = 0 if pad is None else int(pad)
+        st.early_stopping, st.length_penalty = int(self.early_stopping), self.length_penalty
+        st.cand_val, st.cand_tok, st.beam_scores, st.hist = _ptr(self.cand_val), _ptr(self.cand_tok), _ptr(self.beam_scores), _ptr(self.hist)
+        st.slot_tbl = _ptr(slot_tbl)
+        st.ids_next, st.beam_idx, st.done, st.hyp_n = _ptr(self.ids_next), _ptr(self.beam_idx), _ptr(self.done), _ptr(self.hyp_n)
+        st.hyp_score, st.hyp_len, st.hyp_tok, st.worst = _ptr(self.hyp_score), _ptr(self.hyp_len), _ptr(self.hyp_tok), _ptr(self.worst)
+        st.done_count = _ptr(self.done_count)
+        self.state = st
+
+    def reset(self, decoder_start_token_id):
+        self.beam_scores.copy_(self.init_scores.view(-1))
+        self.hist.zero_()
+        self.hist[:, 0] = decoder_start_token_id
+        self.ids_next.fill_(decoder_start_token_id)
+        self.done.zero_(); self.hyp_n.zero_(); self.done_count.zero_()
+        self.worst.fill_(1e9)
+
+    def step(self, lib, logits, cur_len, force_token, ban_eos, stream):
+        L.check(lib.kmb_beam_step(logits.data_ptr(), logits.stride(0), ctypes.byref(self.state), int(cur_len), int(force_token), int(ban_eos),
+                                  stream), "kmb_beam_step")
+
+    def all_done(self):
+        return int(self.done_count.item()) >= self.batch
+
+    def finalize(self, hyp_cls, cur_len, num_return_sequences, max_length):
+        """HF-3.0.2 _generate_beam_search epilogue: open beams of unfinished batch elements become hypotheses, the
+        num_return_sequences best of every element are padded into one LongTensor."""
+        nb = self.num_beams
+        done = self.done.cpu().tolist()
+        hyp_n = self.hyp_n.cpu().tolist()
+        hyp_score, hyp_len = self.hyp_score.cpu().tolist(), self.hyp_len.cpu().tolist()
+        hyp_tok = self.hyp_tok.cpu()
+        worst = self.worst.cpu().tolist()
+        hist = self.hist.cpu().long()
+        scores = self.beam_scores.cpu().tolist()
+        best, lengths = [], []
+        for b in range(self.batch):
+            h = hyp_cls(nb, max_length, self.length_penalty, early_stopping=self.early_stopping)
+            h.beams = [(hyp_score[b][i], hyp_tok[b, i, :hyp_len[b][i]].long()) for i in range(hyp_n[b])]
+            h.worst_score = worst[b]
+            if not done[b]:
+                for i in range(nb):
+                    h.add(hist[b * nb + i, :cur_len], scores[b * nb + i])
+            ranked = sorted(h.beams, key=lambda x: x[0])
+            for _ in range(num_return_sequences):
+                hyp = ranked.pop()[1]
+                lengths.append(len(hyp))
+                best.append(hyp)
+        if min(lengths) != max(lengths):
+            assert self.pad is not None, "`Pad_token_id` has to be defined"
+            width = min(max(lengths) + 1, max_length)
+            decoded = torch.full((len(best), width), self.pad, dtype=torch.long)
+            for i, hyp in enumerate(best):
+                decoded[i, :lengths[i]] = hyp
+                if lengths[i] < max_length:
+                    decoded[i, lengths[i]] = self.eos
+        else:
+            decoded = torch.stack(best).long()
+        return decoded.to(self.dev)
+
+
 class DecodeSession:
     def __init__(self, eng, B, Se, rows, max_len, has_pad):
         cfg, dev, d = eng.cfg, eng.device, eng.cfg.d_model
@@ -94,6 +184,8 @@ class DecodeSession:
         self.sent_len = torch.zeros(rows, dtype=torch.int64, device=dev)
         self.sel = None
         self.launches_per_step = 0
+        self.seed = torch.zeros(1, dtype=torch.int64, device=dev)    # multinomial stream of kmb_sample_select, redrawn per generate()
+        self.beam_ctl = {}
 
     # ------------------------------------------------------------------ one-time per generate() call
     def begin(self, enc_hidden, attention_mask, decoder_start_token_id, use_tbl):
@@ -114,6 +206,7 @@ class DecodeSession:
         self.use_tbl = use_tbl
         if use_tbl:
             self.slot_tbl.copy_(self.rows_i32.expand(self.rows, self.max_len))
+        self.seed.random_()     # torch's CUDA generator: torch.manual_seed() makes sampling reproducible
         self.ids.fill_(decoder_start_token_id)
         self.out.zero_()
         self.out[:, 0] = decoder_start_token_id
@@ -224,34 +317,36 @@ class DecodeSession:
                                                    self.sent_len.data_ptr(), self.out.data_ptr(), self.max_len, self.ids.data_ptr(),
                                                    torch.cuda.current_stream(self.eng.device).cuda_stream), "kmb_greedy_select")
             return
-        if sel["eos"] is not None and cur_len < sel["min_length"]:
-            logits[:, sel["eos"]] = -float("inf")
-        if sel["do_sample"]:
-            scores = logits / sel["temperature"] if sel["temperature"] != 1.0 else logits
-            # HF-3.0.2 top_k_top_p_filtering: top_k == 0 means "no top-k filter" (sample over the whole vocabulary)
-            k = min(sel["top_k"], logits.shape[-1]) if sel["top_k"] > 0 else logits.shape[-1]
-            vals, idx = torch.topk(scores, k, dim=-1)       # top-k filter + softmax == softmax over the k survivors
-            probs = torch.softmax(vals, dim=-1)
-            pick = torch.multinomial(probs, num_samples=1)
-            nxt = idx.gather(-1, pick).squeeze(1)
-        else:
-            nxt = torch.argmax(logits, dim=-1)
-        if sel["eos"] is not None:
-            tok = nxt * self.unfinished + sel["pad"] * (1 - self.unfinished)
-        else:
-            tok = nxt
-        self.out[:, cur_len] = tok
-        self.ids.copy_(tok)
-        if sel["eos"] is not None:
-            is_eos = (tok == sel["eos"]).to(torch.int64)
-            newly = self.unfinished * is_eos
-            self.sent_len.copy_(torch.where(newly.bool(), torch.full_like(self.sent_len, cur_len + 1), self.sent_len))
-            self.unfinished.mul_(1 - is_eos)
+        # top-k (or unfiltered, top_k == 0) multinomial sampling: one kernel per step (csrc/decode_control.cu)
+        eos = -1 if sel["eos"] is None else int(sel["eos"])
+        pad_id = 0 if sel["pad"] is None else int(sel["pad"])
+        L.check(self.eng.lib.kmb_sample_select(logits.data_ptr(), logits.shape[1], self.rows, logits.shape[1], float(sel["temperature"]),
+                                               int(sel["top_k"]), eos, pad_id, int(eos >= 0 and cur_len < sel["min_length"]), cur_len,
+                                               self.seed.data_ptr(), self.unfinished.data_ptr(), self.sent_len.data_ptr(), self.out.data_ptr(),
+                                               self.max_len, self.ids.data_ptr(), torch.cuda.current_stream(self.eng.device).cuda_stream),
+                "kmb_sample_select")
 
-    def step(self, t, flb, sel=None):
-        """Replay (or first capture) the graph of step t.  sel = None: model chain only (beam search reads
-        self.logits and drives the bookkeeping itself); else greedy / sampling selection is part of the graph."""
-        key = (t, None if sel is None else tuple(sorted(sel.items())), self.use_tbl)
+    def beam_controller(self, num_beams, early_stopping, length_penalty, eos, pad):
+        key = (num_beams, bool(early_stopping), float(length_penalty), eos, pad)
+        ctl = self.beam_ctl.get(key)
+        if ctl is None:
+            ctl = BeamController(self.eng.device, self.rows // num_beams, num_beams, self.eng.cfg.vocab_size, self.max_len, eos, pad,
+                                 early_stopping, length_penalty, slot_tbl=self.slot_tbl, ids_next=self.ids)
+            self.beam_ctl[key] = ctl
+        return ctl
+
+    def step(self, t, flb, sel=None, beam=None):
+        """Replay (or first capture) the graph of step t.  sel: greedy / sampling selection is part of the graph;
+        beam = (BeamController, force_token, ban_eos): the device-side beam step is part of the graph; neither: model chain
+        + LM head only (callers read self.logits)."""
+        key = (t, None if sel is None else tuple(sorted(sel.items())), self.use_tbl,
+               None if beam is None else (id(beam[0]), beam[1], beam[2]))
+
+        def select():
+            if sel is not None:
+                self._select_greedy_or_sample(t, sel)
+            if beam is not None:
+                beam[0].step(self.eng.lib, self.logits, t + 1, beam[1], beam[2], torch.cuda.current_stream(self.eng.device).cuda_stream)
         g = self.graphs.get(key)
         if g is None:
             self.flb = flb.reshape(-1)
@@ -260,15 +355,20 @@ class DecodeSession:
             # warm-up run on a side stream (sets function attributes, lets torch ops pick their workspaces)
             s = torch.cuda.Stream(device=self.eng.device)
             s.wait_stream(torch.cuda.current_stream(self.eng.device))
-            snapshot = (self.ids.clone(), self.out.clone(), self.unfinished.clone(), self.sent_len.clone())
+            snapshot = [self.ids.clone(), self.out.clone(), self.unfinished.clone(), self.sent_len.clone(), self.slot_tbl.clone()]
+            saved = [self.ids, self.out, self.unfinished, self.sent_len, self.slot_tbl]
+            if beam is not None:
+                c = beam[0]
+                saved += [c.beam_scores, c.hist, c.done, c.hyp_n, c.hyp_score, c.hyp_len, c.hyp_tok, c.worst, c.done_count]
+                snapshot += [x.clone() for x in saved[5:]]
             with torch.cuda.stream(s):
                 plan.stream = s.cuda_stream
                 self._emit_step(plan, t)
                 plan.run()
-                if sel is not None:
-                    self._select_greedy_or_sample(t, sel)
+                select()
             torch.cuda.current_stream(self.eng.device).wait_stream(s)
-            self.ids.copy_(snapshot[0]); self.out.copy_(snapshot[1]); self.unfinished.copy_(snapshot[2]); self.sent_len.copy_(snapshot[3])
+            for dst, src in zip(saved, snapshot):
+                dst.copy_(src)
             g = torch.cuda.CUDAGraph()
             # destructors of unrelated objects (e.g. the graphs of a discarded model) must not run inside the capture
             gc.collect()
@@ -280,8 +380,7 @@ class DecodeSession:
                     cap.stream = torch.cuda.current_stream(self.eng.device).cuda_stream
                     self._emit_step(cap, t)
                     cap.run()
-                    if sel is not None:
-                        self._select_greedy_or_sample(t, sel)
+                    select()
             finally:
                 if gc_was_enabled:
                     gc.enable()

@@ -58,6 +58,14 @@ class DecodeStepC(C.Structure):
                 + [("layers", DecodeLayer * DECODE_MAX_LAYERS)])
 
 
+class BeamState(C.Structure):
+    """Mirror of struct KmbBeamState."""
+    _fields_ = ([(n, C.c_int32) for n in ("batch", "num_beams", "K", "V", "eos", "pad", "max_len", "early_stopping")]
+                + [("length_penalty", C.c_double)]
+                + [(n, c_void_p) for n in ("cand_val", "cand_tok", "beam_scores", "hist", "slot_tbl", "ids_next", "beam_idx", "done",
+                                           "hyp_n", "hyp_score", "hyp_len", "hyp_tok", "worst", "done_count")])
+
+
 # name -> argtypes; every function returns int except those listed in _RESTYPES
 _PROTOS = {
     "kmb_version": [],
@@ -84,6 +92,10 @@ _PROTOS = {
     "kmb_decode_pack_weights": [C.POINTER(DecodeLayer), c_int, c_int, c_int, c_void_p, c_void_p],
     "kmb_greedy_select": [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                           c_void_p, c_void_p],
+    "kmb_select_max_vocab": [],
+    "kmb_sample_select": [c_void_p, c_int64, c_int, c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_int64, c_void_p, c_void_p],
+    "kmb_beam_step": [c_void_p, c_int64, C.POINTER(BeamState), c_int, c_int, c_int, c_void_p],
     "kmb_attn_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                      c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],

@@ -182,8 +182,8 @@ class GenerationMixin:
         # Same token semantics as the legacy loops below; knobs the decode chain does not implement fall through.
         fast_ok = (use_cache and repetition_penalty == 1.0 and no_repeat_ngram_size == 0 and bad_words_ids is None
                    and not model_specific_kwargs and max_length <= 256 and input_ids.shape[1] <= 256
-                   and ((num_beams == 1 and (not do_sample or top_p == 1.0)) or (num_beams > 1 and not do_sample))
-                   and getattr(self, "_fast_generate", True) and self.precision != "fp32")
+                   and ((num_beams == 1 and (not do_sample or top_p == 1.0)) or (num_beams > 1 and not do_sample and max_length > 2))
+                   and getattr(self, "_fast_generate", True) and self.precision != "fp32" and self._select_kernels_fit(num_beams))
         if fast_ok:
             return self._generate_fast(encoder_outputs[0], attention_mask, batch_size, effective_batch_size, effective_batch_mult,
                                        num_beams, max_length, min_length, do_sample, early_stopping, temperature, top_k,
@@ -221,11 +221,17 @@ class GenerationMixin:
         return self._generate_no_beam_search(input_ids, **common)
 
 
+    def _select_kernels_fit(self, num_beams):
+        """the sampling / beam controllers keep one logits row in a CTA's shared memory"""
+        from kmbart import lib as L
+        return self.config.vocab_size <= L.load().kmb_select_max_vocab() and 2 * num_beams <= self.config.vocab_size and num_beams <= 64
+
     # ------------------------------------------------------------------ fast decode (same semantics, device-side loop)
     def _generate_fast(self, enc_hidden, attention_mask, batch_size, effective_batch_size, effective_batch_mult, num_beams,
                        max_length, min_length, do_sample, early_stopping, temperature, top_k, pad_token_id, eos_token_id,
                        length_penalty, num_return_sequences, decoder_start_token_id, vocab_size):
         from kmbart.decode import get_session
+        cfg = self.config
         eng = self._engine()
         eng.sync_shadow()
         B, Se = enc_hidden.shape[0], enc_hidden.shape[1]
@@ -250,14 +256,22 @@ class GenerationMixin:
                 beyond = torch.arange(width, device=decoded.device).unsqueeze(0) >= sent_len.unsqueeze(1)
                 decoded[beyond] = pad_token_id
             return decoded
-        input_ids = torch.full((rows, 1), decoder_start_token_id, dtype=torch.long, device=enc_hidden.device)
-        return self._generate_beam_search(input_ids, cur_len=1, max_length=max_length, min_length=min_length, do_sample=False,
-                                          early_stopping=early_stopping, temperature=temperature, top_k=top_k, top_p=1.0,
-                                          repetition_penalty=1.0, no_repeat_ngram_size=0, bad_words_ids=None,
-                                          pad_token_id=pad_token_id, eos_token_id=eos_token_id, batch_size=effective_batch_size,
-                                          num_return_sequences=num_return_sequences, length_penalty=length_penalty,
-                                          num_beams=num_beams, vocab_size=vocab_size, encoder_outputs=None, attention_mask=None,
-                                          use_cache=True, model_specific_kwargs={}, sess=sess)
+        # ---- beam search: model step + LM head + device-side beam controller in one graph per token; the host only polls
+        # "every batch element done" every fourth step and finalises the hypotheses once at the end
+        ctl = sess.beam_controller(num_beams, early_stopping, length_penalty, eos_token_id, pad_token_id)
+        ctl.reset(decoder_start_token_id)
+        steps = max_length - 1
+        cur_len = 1
+        for t in range(steps):
+            cur_len = t + 1
+            # adjust_logits_during_generation (src/model/mixins.py:386-402): BOS forced at cur_len 1, EOS at max_length - 1
+            force = cfg.bos_token_id if cur_len == 1 else (cfg.eos_token_id if (cur_len == max_length - 1 and cfg.eos_token_id is not None) else -1)
+            ban = int(eos_token_id is not None and cur_len < min_length)
+            sess.step(t, flb, None, beam=(ctl, int(force), ban))
+            cur_len = t + 2
+            if eos_token_id is not None and (t % 4 == 3) and t + 1 < steps and ctl.all_done():
+                break
+        return ctl.finalize(BeamHypotheses, cur_len, num_return_sequences, max_length)
 
     # ------------------------------------------------------------------ loops (HF-3.0.2 generation_utils semantics)
     def _use_cache(self, outputs, use_cache):
