@@ -27,6 +27,16 @@ import torch  # noqa: E402
 FLOP_PER_SAMPLE = 56.412e9   # 18.804 GFLOP fwd x 3
 B_PER_GPU, R, N_CTX, S_D = 128, 36, 64, 48
 METRIC = "train samples/s KM-BART-base VCG fine-tune step (fwd+bwd+AdamW)"
+# The other training configurations of BASELINE.json: measured by the same run as short extra legs
+# (`workloads` in the JSON line) so that the driver's 1/2/4/8-GPU runs carry them too, or alone with --workload.
+WORKLOADS = {
+    "vcg": dict(config="configs/vcg_base.json", cls="MultiModalBartForConditionalGeneration", batch=128, R=36, n_ctx=64, tgt=48,
+                flop=56.412e9, label="configs[1]: KM-BART base VCG fine-tuning step"),
+    "pretrain": dict(config="configs/pretrain_base.json", cls="MultiModalBartForPreTraining", batch=128, R=36, n_ctx=64, tgt=48,
+                     flop=77.012e9, label="configs[2]: KM-BART base multitask pre-training step (MLM x5 + MRM + attribute + relation heads, S_d = 86)"),
+    "large": dict(config=None, cls="MultiModalBartForConditionalGeneration", batch=64, R=100, n_ctx=256, tgt=48,
+                  flop=464.662e9, label="configs[4]: KM-BART large (12+12, d = 1024) VCG step, 100 RoIs + 256 ctx tokens (S_e = 356)"),
+}
 
 
 def load_peaks():
@@ -68,8 +78,8 @@ class ClockSampler(threading.Thread):
 
 
 def make_batch(cfg, seed, device=None, pin=False, batch=B_PER_GPU):
-    from oracle import kmbart_oracle as O   # synthetic-batch generator only; not on the timed path
-    b = O.synthetic_batch(cfg, batch=batch, n_regions=R, n_ctx=N_CTX, tgt_len=S_D, seed=seed)
+    from kmbart.synth import synthetic_batch   # product-side generator; the oracle is not imported by this arm
+    b = synthetic_batch(cfg, batch=batch, n_regions=R, n_ctx=N_CTX, tgt_len=S_D, seed=seed)
     if pin:
         b = {k: ([t.pin_memory() for t in v] if isinstance(v, list) else v.pin_memory()) for k, v in b.items()}
     if device is not None:
@@ -159,7 +169,135 @@ def bench_generation(model, cfg, dev, rank, world, dist, hbm_peak, peak_src):
     return out
 
 
+def bench_workload(name, dev, rank, world, dist, steps, sustained, e2e=False):
+    """One of the other BASELINE configs, device-resident inputs, fwd + bwd + AdamW, CUDA events, max over ranks."""
+    import gc
+    from src.model.config import MultiModalBartConfig
+    import src.model.model as M
+    from kmbart.optim import AdamW
+    from kmbart.synth import synthetic_batch, synthetic_pretrain_batch, to_device
+    w = WORKLOADS[name]
+    if w["config"]:
+        with open(os.path.join(ROOT, w["config"])) as f:
+            cfg = MultiModalBartConfig.from_dict(json.load(f))
+    else:
+        cfg = MultiModalBartConfig()      # src/model/config.py:12-18 defaults = bart-large
+    torch.manual_seed(0)
+    model = getattr(M, w["cls"])(cfg).to(dev).train()
+    if world > 1:
+        from kmbart.parallel import FlatGradReducer
+        model._engine()
+        FlatGradReducer(model, defer_tail=True)
+    opt = AdamW(model.parameters(), lr=1e-5)
+    gen = synthetic_pretrain_batch if name == "pretrain" else synthetic_batch
+    batch = to_device(gen(cfg, batch=w["batch"], n_regions=w["R"], n_ctx=w["n_ctx"], tgt_len=w["tgt"], seed=1234 + rank), dev)
+
+    def step():
+        out = model(**batch)
+        loss = out[0]["loss"] if isinstance(out[0], dict) else out[0]
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+    for _ in range(3):
+        step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    value = w["batch"] * world * steps / (ms * 1e-3)
+    res = {"workload": w["label"], "value": round(value, 1), "unit": "samples/s", "ms_per_step": round(ms / steps, 3), "steps": steps,
+           "batch_per_gpu": w["batch"], "n_gpus": world, "step_mfu": round(value / world * w["flop"] / 1e12 / sustained, 4),
+           "loss": float(loss.item()), "gpu_launches": int(model._engine().launches_last + opt.launches_last)}
+    if e2e:
+        host = to_device(gen(cfg, batch=w["batch"], n_regions=w["R"], n_ctx=w["n_ctx"], tgt_len=w["tgt"], seed=1234 + rank), None, pin=True)
+        h2d = sum((sum(t.numel() * t.element_size() for t in v) if isinstance(v, list) and v and torch.is_tensor(v[0]) else
+                   (v.numel() * v.element_size() if torch.is_tensor(v) else 0)) for v in host.values())
+
+        def e2e_step():
+            b = {k: (v if k == "relation_labels" else ([t.to(dev, non_blocking=True) for t in v] if isinstance(v, list) else v.to(dev, non_blocking=True)))
+                 for k, v in host.items()}
+            out = model(**b)
+            l_ = out[0]["loss"] if isinstance(out[0], dict) else out[0]
+            opt.zero_grad()
+            l_.backward()
+            opt.step()
+            return l_.item()
+        e2e_step()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            e2e_step()
+        e1.record()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms2], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms2 = t.item()
+        res["e2e"] = {"value": round(w["batch"] * world * steps / (ms2 * 1e-3), 1), "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
+                      "d2h_bytes_per_step": 4, "ms_per_step": round(ms2 / steps, 3),
+                      "api": "pinned host batch -> non_blocking .to(device) -> model.forward(**batch) + loss.backward() + AdamW.step(), loss.item() each step"}
+    del model, opt, batch
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_other_workload(args):
+    """--workload pretrain | large as the headline of the JSON line (same contract; e2e = pinned host batch copied every
+    step with non_blocking .to(device) on the compute stream + loss.item())."""
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    burst, sustained, hbm, peak_src = load_peaks()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    res = bench_workload(args.workload, dev, rank, world, dist, args.steps, sustained, e2e=True)
+    sampler.stop_flag = True
+    if rank == 0:
+        sampler.join(timeout=2)
+        w = WORKLOADS[args.workload]
+        line = {"metric": "train samples/s " + w["label"], "value": res["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": 3, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": w["label"], "global_batch": w["batch"] * world, "parallelism": f"dp{world}",
+                           "l2": "per-step working set far exceeds the 126 MB L2"},
+                "e2e": res["e2e"], "gpu_launches": res["gpu_launches"] * args.steps,
+                "roofline": {"bound": "tensor", "kernel": "whole step (all tcgen05 GEMMs + attention)", "achieved": round(res["value"] / world * w["flop"] / 1e12, 1),
+                             "peak": sustained, "unit": "TFLOP/s", "frac": res["step_mfu"], "traffic": None, "peak_source": peak_src + " sustained"},
+                "cpu_baseline": None, "clocks": sampler.summary(), "loss": res["loss"]}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def run_ours(args):
+    if args.workload != "vcg":
+        return run_other_workload(args)
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -258,18 +396,24 @@ def run_ours(args):
               for v in host_batch.values())
     assert h2d_seen and h2d_seen[-1] == h2d, "the feeder must move the whole batch every step"
 
-    # ---- dominant kernel: the tcgen05 GEMM, timed alone with CUDA events on the launch stream
+    # ---- dominant kernel: the tcgen05 GEMM.  Timed alone (CUDA events on the launch stream, L2 flushed between launches)
+    # in EXACTLY the form the step launches it most expensively: encoder fc1 = bias + exact-erf GELU + bf16 output + bf16
+    # pre-activation copy (16 epilogue warps), 12800 x 3072 x 768 — 12 such launches per step (6 encoder layers fwd; the
+    # decoder ones have M = 6144).  The step-level figure next to it is step_mfu (whole step vs the sustained peak).
     burst, sustained, hbm, peak_src = load_peaks()
     roof = None
     if rank == 0:
         import ctypes as C
-        M, N, K = B_PER_GPU * (R + N_CTX), cfg.encoder_ffn_dim, cfg.d_model   # fc1 of one encoder layer
+        M, N, K = B_PER_GPU * (R + N_CTX), cfg.encoder_ffn_dim, cfg.d_model
         A = torch.randn(M, K, device=dev).to(torch.bfloat16)
         W = torch.randn(N, K, device=dev).to(torch.bfloat16)
+        bias = torch.randn(N, device=dev)
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        pre = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
         e = L.GemmEpilogue()
-        e.alpha, e.out_bf16, e.ld_bf16 = 1.0, out.data_ptr(), N
+        e.alpha, e.act, e.bias = 1.0, L.ACT_GELU, bias.data_ptr()
+        e.out_bf16, e.ld_bf16, e.out_preact = out.data_ptr(), N, pre.data_ptr()
         lib = L.load()
         stream = torch.cuda.current_stream(dev).cuda_stream
         tot = 0.0
@@ -285,16 +429,24 @@ def run_ours(args):
                 tot += e0.elapsed_time(e1)
         gemm_ms = tot / iters
         ach = 2.0 * M * N * K / (gemm_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_tc05_kernel<256> fc1 12800x3072x768", "achieved": round(ach, 1),
-                "peak": burst, "unit": "TFLOP/s", "frac": round(ach / burst, 4),
-                # DRAM bytes of ONE launch of this kernel from the ncu --set full capture committed as
-                # profiles/r01k_ncu_gemm_fc1_plain_summary.txt (dram__bytes_read.sum 24.75 MB + dram__bytes_write.sum
-                # 32.03 MB; algorithmic: 24.4 MB operands + 78.6 MB output, most of which is still dirty in L2 at kernel end)
-                "traffic": 56780288, "traffic_unit": "bytes/launch (ncu, profiles/r01k_ncu_gemm_fc1_plain_summary.txt)",
-                "peak_source": peak_src + " burst (kernel timed alone, L2 flushed between launches)",
-                "step_mfu": None}
+        roof = {"bound": "tensor", "kernel": "gemm_tc05_kernel<256,...,ES=4> encoder fc1 + bias + GELU + pre-activation copy, 12800x3072x768 (as launched in the step)",
+                "achieved": round(ach, 1), "peak": burst, "unit": "TFLOP/s", "frac": round(ach / burst, 4), "traffic": None,
+                "us_per_launch": round(gemm_ms * 1e3, 2),
+                "peak_source": peak_src + " burst (kernel timed alone, L2 flushed between launches)", "step_mfu": None}
+        del A, W, out, pre, flush
 
     gen = None if args.train_only else bench_generation(model, cfg, dev, rank, world, dist, hbm, peak_src)
+    extra = {}
+    if not args.train_only and args.workload == "vcg":
+        del model, opt, dev_batch
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        for name, k in (("pretrain", 6), ("large", 4)):
+            try:
+                extra[name] = bench_workload(name, dev, rank, world, dist, k, sustained)
+            except Exception as ex:   # an extra leg must never take the headline line down
+                extra[name] = {"error": repr(ex)[:200]}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -318,23 +470,56 @@ def run_ours(args):
                 "ms_per_step": round(ms_e2e / args.steps, 3), "api": "kmbart.feed.DeviceFeeder (pinned list-of-tensors batch -> side-stream H2D, one batch per step, overlapped with the previous step) -> model.forward(**batch) + loss.backward() + AdamW.step(), loss.item() each step"},
         "gpu_launches": int(launches_step * args.steps),
         "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary(), "loss": last.get("loss"), "gen": gen,
+        "workloads": extra,
     }
+    if gen is not None:   # the decode step against the HBM roofline, next to the training roofline
+        for key in ("rows64_greedy", "rows320_beam5"):
+            d = gen["decode_step"][key]
+            line["roofline_decode_" + key.split("_")[0]] = {
+                "bound": "hbm", "kernel": "persistent decode step + LM head" + (" + greedy select" if "greedy" in key else ""),
+                "achieved": d["achieved_GBps"], "peak": hbm, "unit": "GB/s", "frac": d["frac_of_hbm_peak"], "traffic": None,
+                "us_per_step": d["us_per_step"], "algorithmic_bytes_per_step": d["algorithmic_bytes_per_step"], "peak_source": peak_src}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
 
-def _oracle_train_step_fn(batch_size):
-    """The reference's CPU path (oracle restatement): forward + CE + backward + HF-AdamW, fp32."""
+_REF_CFG_KEYS = ["vocab_size", "d_model", "image_feature_size", "encoder_layers", "decoder_layers", "encoder_attention_heads",
+                 "decoder_attention_heads", "encoder_ffn_dim", "decoder_ffn_dim", "max_position_embeddings", "dropout", "init_std"]
+
+
+def _cpu_train_step_fn(batch_size):
+    """The reference's CPU path: forward + CE + backward + HF-AdamW in fp32, returns (step_fn, kind).
+    kind "reference": the reference's OWN src/model classes (imported from /root/reference through oracle/hf302_shim.py,
+    which stands in for the un-installable transformers==3.0.2) — only where that checkout exists (the build container);
+    kind "port": the oracle's functional restatement of the same code (the GPU box has no /root/reference)."""
     from oracle import kmbart_oracle as O
     cfg = O.base_config()
+    batch = O.synthetic_batch(cfg, batch=batch_size, n_regions=R, n_ctx=N_CTX, tgt_len=S_D, seed=1234)
+    if os.path.isdir("/root/reference/src/model") and os.environ.get("KMBART_REFERENCE_ARM", "auto") != "port":
+        try:
+            from oracle import hf302_shim as S
+            mods = S.import_reference()
+            torch.manual_seed(0)
+            model = mods["model"].MultiModalBartForConditionalGeneration(
+                mods["config"].MultiModalBartConfig(**{k: getattr(cfg, k) for k in _REF_CFG_KEYS})).train()
+            opt = S.AdamW(model.parameters(), lr=1e-5)      # HF-3.0.2 transformers.AdamW as constructed at vcg_train.py:100
+
+            def ref_step():
+                loss = model(**batch)[0]
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                return loss.item()
+            return ref_step, "reference"
+        except Exception as ex:   # fall back to the port, say why
+            print(f"bench.py: reference import failed ({ex!r}); timing the oracle port instead", file=sys.stderr)
     sd = O.init_state_dict(cfg, seed=0)
     names = [k for k in sd if k != "final_logits_bias"]
     for k in names:
         sd[k].requires_grad_(True)
     m = [torch.zeros_like(sd[k]) for k in names]
     v = [torch.zeros_like(sd[k]) for k in names]
-    batch = O.synthetic_batch(cfg, batch=batch_size, n_regions=R, n_ctx=N_CTX, tgt_len=S_D, seed=1234)
     state = {"t": 0}
 
     def step():
@@ -346,20 +531,21 @@ def _oracle_train_step_fn(batch_size):
         with torch.no_grad():
             O.adamw_step([sd[k] for k in names], [sd[k].grad for k in names], m, v, state["t"], lr=1e-5)
         return loss.item()
-    return step
+    return step, "port"
 
 
 def cpu_baseline(sample_steps=1, batch_size=16):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = _oracle_train_step_fn(batch_size)
+    step, kind = _cpu_train_step_fn(batch_size)
     step()   # warm-up
     t0 = time.perf_counter()
     for _ in range(sample_steps):
         step()
     dt = time.perf_counter() - t0
-    return {"value": round(batch_size * sample_steps / dt, 2), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{sample_steps} fwd+bwd+AdamW step(s) of the CPU oracle at batch {batch_size} (same shapes, fp32)"}
+    what = "the reference's own src/model (through the HF-3.0.2 shim)" if kind == "reference" else "the CPU oracle (port of the reference path)"
+    return {"value": round(batch_size * sample_steps / dt, 2), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{sample_steps} fwd+bwd+AdamW step(s) of {what} at batch {batch_size} (same shapes, fp32)"}
 
 
 def run_reference(args):
@@ -369,7 +555,7 @@ def run_reference(args):
     bs = 16
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = _oracle_train_step_fn(bs)
+    step, kind = _cpu_train_step_fn(bs)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -383,9 +569,10 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1] shapes; each step is a bounded sample (batch 16 of the 128) of the reference's "
-                               "CPU path: oracle restatement of src/model + HF-3.0.2 BART, fwd+bwd+AdamW",
+                               "CPU path (the reference's own src/model where /root/reference exists, else the oracle restatement of "
+                               "src/model + HF-3.0.2 BART), fwd+bwd+AdamW",
                    "global_batch": bs, "parallelism": "cpu"},
-        "cpu_baseline": {"value": round(value, 2), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+        "cpu_baseline": {"value": round(value, 2), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
                          "sample": f"batch {bs} per step, {args.steps} steps"},
         "e2e": {"value": round(value, 2), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "loss": loss,
@@ -401,6 +588,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--train-only", action="store_true", help="experiments: skip the generation legs and the CPU baseline")
     ap.add_argument("--ddp", action="store_true", help="N > 1: wrap in torch DDP (reference scripts' way) instead of FlatGradReducer")
+    ap.add_argument("--workload", default="vcg", choices=sorted(WORKLOADS), help="vcg = configs[1] (headline, default; also runs short "
+                    "pretrain / large legs); pretrain = configs[2]; large = configs[4] as the headline of the line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -19,8 +19,8 @@ torch.manual_seed(0)
 model = MultiModalBartForConditionalGeneration(cfg).cuda().train()
 opt = AdamW(model.parameters(), lr=1e-5)
 if large:
-    from oracle import kmbart_oracle as O   # synthetic-batch generator only
-    b = O.synthetic_batch(cfg, batch=64, n_regions=100, n_ctx=256, tgt_len=48, seed=1234)
+    from kmbart.synth import synthetic_batch
+    b = synthetic_batch(cfg, batch=64, n_regions=100, n_ctx=256, tgt_len=48, seed=1234)
     batch = {k: ([t.cuda() for t in v] if isinstance(v, list) else v.cuda()) for k, v in b.items()}
 else:
     batch = bench.make_batch(cfg, 1234, device="cuda")

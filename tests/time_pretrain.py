@@ -5,7 +5,7 @@ import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "km-bart_b200"))
 import torch
-from oracle import kmbart_oracle as O   # synthetic-batch generator only; not on the timed path
+from kmbart.synth import synthetic_batch
 from src.model.config import MultiModalBartConfig
 from src.model.model import MultiModalBartForPreTraining
 from kmbart.optim import AdamW
@@ -16,7 +16,7 @@ B, R, T = 128, 36, 48
 torch.manual_seed(0)
 model = MultiModalBartForPreTraining(cfg).cuda().train()
 opt = AdamW(model.parameters(), lr=1e-5)
-batch = O.synthetic_batch(cfg, batch=B, n_regions=R, n_ctx=64, tgt_len=T, seed=1234)
+batch = synthetic_batch(cfg, batch=B, n_regions=R, n_ctx=64, tgt_len=T, seed=1234)
 g = torch.Generator().manual_seed(9)
 Sd = R + 2 + T
 dec = torch.full((B, Sd), cfg.pad_token_id, dtype=torch.long)

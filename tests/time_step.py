@@ -11,7 +11,7 @@ from kmbart.optim import AdamW
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 large = len(sys.argv) > 2 and sys.argv[2] == "large"   # BASELINE configs[4]: d=1024 12+12, 100 RoIs + 256 ctx tokens, batch 64/GPU
 if large:
-    from oracle import kmbart_oracle as O   # synthetic-batch generator only
+    from kmbart.synth import synthetic_batch
     cfg = MultiModalBartConfig(max_position_embeddings=1024)
     BATCH, FLOP_PER_SAMPLE = 64, 464.662e9
 else:
@@ -21,7 +21,7 @@ torch.manual_seed(0)
 model = MultiModalBartForConditionalGeneration(cfg).cuda().train()
 opt = AdamW(model.parameters(), lr=1e-5)
 if large:
-    b = O.synthetic_batch(cfg, batch=BATCH, n_regions=100, n_ctx=256, tgt_len=48, seed=1234)
+    b = synthetic_batch(cfg, batch=BATCH, n_regions=100, n_ctx=256, tgt_len=48, seed=1234)
     batch = {k: ([t.cuda() for t in v] if isinstance(v, list) else v.cuda()) for k, v in b.items()}
 else:
     batch = bench.make_batch(cfg, 1234, device="cuda")
