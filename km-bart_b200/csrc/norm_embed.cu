@@ -49,6 +49,13 @@ __global__ void __launch_bounds__(256) pack_features_kernel(const float* const* 
   pdl_wait();
   const int r = blockIdx.x;
   if (r >= R) return;
+  if (row_off && r >= row_off[B]) {
+    // R is the CAPACITY of the packed buffers; rows past the batch's region count stay zero (GEMM rows / K-reductions /
+    // column sums over them contribute nothing)
+    *reinterpret_cast<uint4*>(feats + (int64_t)r * FEAT + threadIdx.x * 8) = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) *reinterpret_cast<float4*>(boxes + (int64_t)r * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
   const float* src;
   if (ptrs) {
     int lo = 0, hi = B;  // largest b with row_off[b] <= r

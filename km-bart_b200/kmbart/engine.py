@@ -15,6 +15,7 @@ residual stream next to bf16 GEMM operands, fused QKV / cross-KV projections.
 import ctypes as C
 import math
 import os
+from collections import OrderedDict
 
 import torch
 
@@ -192,8 +193,14 @@ class Engine:
         self.model = model
         self.store = ParamStore(model)
         self.device = self.store.device
+        # workspaces ("arenas": activation stash + staging buffers of one input shape; decode sessions) and their launch
+        # plans, least recently used first.  The reference's collator pads to the longest sequence of each batch
+        # (src/data/collation.py:68-213), so shapes keep changing: at most KMBART_MAX_ARENAS workspaces stay resident, the
+        # oldest is dropped (its memory returns to torch's caching allocator and is reused by the next one).
         self.plans = {}
-        self.arenas = {}
+        self.arenas = OrderedDict()
+        self.max_arenas = max(2, int(os.environ.get("KMBART_MAX_ARENAS", "8")))
+        self._fwd_serial = 0
         d = config.d_model
         assert d % 64 == 0 and d <= 1024, "d_model must be a multiple of 64 and <= 1024"
         assert d // config.encoder_attention_heads == 64 and d // config.decoder_attention_heads == 64, \
@@ -235,8 +242,23 @@ class Engine:
         a = self.arenas.get(key)
         if a is None:
             a = {}
-            self.arenas[key] = a
+            self.remember(key, a)
         return a
+
+    def remember(self, key, a):
+        """Register a workspace as most recently used; evict beyond the bound (workspace + its plans / graphs)."""
+        self.arenas[key] = a
+        self.arenas.move_to_end(key)
+        while len(self.arenas) > self.max_arenas:
+            old, _ = self.arenas.popitem(last=False)
+            self.plans.pop(old, None)
+
+    def touch(self, key):
+        if key in self.arenas:
+            self.arenas.move_to_end(key)
+
+    def _seed_ptr(self):
+        return getattr(self, "_cur_seed", self.seed).data_ptr()
 
     @staticmethod
     def buf(a, name, shape, dtype):
@@ -263,7 +285,7 @@ class Engine:
         e.out_preact = _ptr(kw.get("out_preact"))
         e.dropout_p = kw.get("dropout_p", 0.0)
         e.dropout_tag = kw.get("dropout_tag", 0)
-        e.dropout_seed = self.seed.data_ptr() if e.dropout_p > 0 else 0
+        e.dropout_seed = self._seed_ptr() if e.dropout_p > 0 else 0
         e.labels = _ptr(kw.get("labels"))
         e.ce_max, e.ce_sum = _ptr(kw.get("ce_max")), _ptr(kw.get("ce_sum"))
         e.ce_label_logit, e.ce_lse, e.ce_gscale = _ptr(kw.get("ce_label_logit")), _ptr(kw.get("ce_lse")), _ptr(kw.get("ce_gscale"))
@@ -279,14 +301,14 @@ class Engine:
         st, d = self.store, self.cfg.d_model
         plan.add(self.lib.kmb_layernorm_fwd, _ptr(z_b16), _ptr(residual), _ptr(st.p32(gname + ".weight")),
                  _ptr(st.p32(gname + ".bias")), _ptr(pre), _ptr(out_f32), _ptr(out_b16), _ptr(mean), _ptr(rstd), M, d,
-                 drop[0], drop[1], self.seed.data_ptr(), plan.stream)
+                 drop[0], drop[1], self._seed_ptr(), plan.stream)
 
     def ln_bwd(self, plan, dyA, dyB, pre, mean, rstd, gname, dpre, dz, dbias, M, drop_in=(0.0, 0), drop_out=(0.0, 0)):
         st, d = self.store, self.cfg.d_model
         plan.add(self.lib.kmb_layernorm_bwd, _ptr(dyA), _ptr(dyB), _ptr(pre), _ptr(mean), _ptr(rstd),
                  _ptr(st.p32(gname + ".weight")), _ptr(dpre), _ptr(dz), _ptr(st.g(gname + ".weight")),
                  _ptr(st.g(gname + ".bias")), _ptr(dbias), M, d, drop_in[0], drop_in[1], drop_out[0], drop_out[1],
-                 self.seed.data_ptr(), plan.stream)
+                 self._seed_ptr(), plan.stream)
 
     def attn_fwd(self, plan, q, k, v, ldq, ldk, ldv, o, lse, pad, B, H, Sq, Sk, causal):
         plan.add(self.lib.kmb_attn_fwd, _ptr(q), _ptr(k), _ptr(v), ldq, ldk, ldv, _ptr(o), self.cfg.d_model, _ptr(lse),
@@ -390,7 +412,7 @@ class Engine:
                  _ptr(st.p32(self.n("encoder.layernorm_embedding.weight"))),
                  _ptr(st.p32(self.n("encoder.layernorm_embedding.bias"))), _ptr(emb_pre), _ptr(x_f32), _ptr(x_b16),
                  _ptr(mean), _ptr(rstd), Me, Se, d, cfg.extra_pos_embeddings, 0, scale, p_drop, 1,
-                 self.seed.data_ptr(), plan.stream)
+                 self._seed_ptr(), plan.stream)
         H, F = cfg.encoder_attention_heads, cfg.encoder_ffn_dim
         for l in range(cfg.encoder_layers):
             lp, tag = self.n(f"encoder.layers.{l}"), f"e{l}."
@@ -417,7 +439,7 @@ class Engine:
                  _ptr(st.p32(self.n("decoder.layernorm_embedding.weight"))),
                  _ptr(st.p32(self.n("decoder.layernorm_embedding.bias"))), _ptr(emb_pre), _ptr(x_f32), _ptr(x_b16),
                  _ptr(mean), _ptr(rstd), Md, Sd, d, cfg.extra_pos_embeddings, 0, scale, p_drop, 2,
-                 self.seed.data_ptr(), plan.stream)
+                 self._seed_ptr(), plan.stream)
         H, F = cfg.decoder_attention_heads, cfg.decoder_ffn_dim
         for l in range(cfg.decoder_layers):
             lp, tag = self.n(f"decoder.layers.{l}"), f"d{l}."
@@ -517,8 +539,11 @@ class Engine:
         assert float(cfg.activation_dropout) == 0.0 or not a["training"], "activation_dropout > 0 is not supported"
         fwd = Plan()
         fwd.stream = a["stream"]
+        # the dropout seed of a step lives in ITS workspace: a forward on another shape between this forward and its
+        # backward (two micro-batches, loss_a + loss_b) must not change the masks the backward regenerates
+        self._cur_seed = a["seed"]
         if p_drop > 0:
-            fwd.add(self.lib.kmb_next_seed, _ptr(self.seed_state), _ptr(self.seed), fwd.stream)
+            fwd.add(self.lib.kmb_next_seed, _ptr(self.seed_state), _ptr(a["seed"]), fwd.stream)
         _, enc_b16 = self._encoder_fwd(fwd, a, B, Se, R, True, p_drop)
         self._decoder_fwd(fwd, a, B, Sd, Se, True, p_drop, enc_b16)
         if a["has_lm"]:
@@ -537,6 +562,7 @@ class Engine:
         Me, Md = B * Se, B * Sd
         p_drop = float(cfg.dropout) if a["training"] else 0.0
         acc = int(acc)
+        self._cur_seed = a["seed"]
         bwd = Plan()
         bwd.stream = a["stream"]
         has_lm, with_heads = a["has_lm"], a["with_heads"]
@@ -602,6 +628,8 @@ class Engine:
                 bwd.add(self.grad_reducer.launch_stage, cfg.decoder_layers + cfg.encoder_layers - 1 - l)
         demb_e = dpre_e[flip]
         dvis = self.buf(a, "g.dvis", (max(R, 1), d), BF16)
+        if R > 0:
+            bwd.add(_zero, dvis)     # rows no token points at (capacity tail, unused regions) must read as zero
         self.ln_bwd(bwd, dyA, dyB, a["e.emb_pre"], a["e.emb_mean"], a["e.emb_rstd"], self.n("encoder.layernorm_embedding"), demb_e, None, None, Me,
                     drop_in=(p_drop, 1))
         bwd.add(self.lib.kmb_embed_bwd, _ptr(demb_e), _ptr(a["ids_e"]), _ptr(a["slot"]), _ptr(st.g(self.n("shared.weight"))),
@@ -631,13 +659,23 @@ class Engine:
                 torch.eq(a["ids_d"], cfg.pad_token_id, out=a["pad_d_bool"])
         if labels is not None:
             a["labels"].copy_(labels.reshape(-1))
+        # pinned staging is double-buffered and guarded by events: a host that runs ahead (no loss.item(), the DeviceFeeder
+        # path) must not overwrite a buffer whose host-to-device copy of the previous step has not executed yet
+        i = a["stage_i"] = a.get("stage_i", 0) ^ 1
+        ev = a["stage_ev"][i]
+        if ev is not None:
+            ev.synchronize()
         if isinstance(image_features, torch.Tensor):   # packed [R, 2052] fast path
-            a["packed_buf"].copy_(image_features)
+            a["packed_buf"][:image_features.shape[0]].copy_(image_features)
         else:
             ptrs = [f.data_ptr() for f in image_features]
-            a["feat_ptrs_host"].copy_(torch.tensor(ptrs, dtype=torch.int64))
-            a["feat_ptrs"].copy_(a["feat_ptrs_host"], non_blocking=True)
-        a["row_off"].copy_(a["row_off_host"], non_blocking=True)
+            a["feat_ptrs_host"][i].copy_(torch.tensor(ptrs, dtype=torch.int64))
+            a["feat_ptrs"].copy_(a["feat_ptrs_host"][i], non_blocking=True)
+        a["row_off_host"][i].copy_(torch.tensor(a["row_off_list"], dtype=torch.int32))
+        a["row_off"].copy_(a["row_off_host"][i], non_blocking=True)
+        if ev is None:
+            ev = a["stage_ev"][i] = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
 
     def _get_arena(self, mode, input_ids, image_features, attention_mask, decoder_input_ids, labels, training,
                    lm_factor=1.0, image_counts=None, has_lm=True, with_heads=False):
@@ -656,12 +694,22 @@ class Engine:
                         "image_features must be CUDA fp32 [n_i, 2052] tensors"
         R = sum(counts)
         stream = self.stream()
-        key = (mode, B, Se, Sd, R, attention_mask is not None, bool(training), packed, float(lm_factor), stream,
+        # R (regions in the batch: 10-50 per image in the reference's data) is a CAPACITY of the workspace, not part of its
+        # identity: rows [R, capacity) of the packed features / boxes / visual gradients are kept at zero, which every
+        # consumer (GEMM rows, K-reductions, column sums) ignores.  A batch with more regions grows the workspace.
+        key = (mode, B, Se, Sd, R > 0, attention_mask is not None, bool(training), packed, float(lm_factor), stream,
                bool(has_lm), bool(with_heads))
         a = self.arenas.get(key)
+        grown = 0
+        if a is not None and a["R"] < R:
+            grown = a["R"] * 5 // 4
+            self.arenas.pop(key)
+            self.plans.pop(key, None)
+            a = None
         if a is None:
             dev = self.device
-            a = {"__dev": dev, "B": B, "Se": Se, "Sd": Sd, "R": R, "training": bool(training),
+            cap = (max(R, grown) + 63) // 64 * 64
+            a = {"__dev": dev, "B": B, "Se": Se, "Sd": Sd, "R": cap, "training": bool(training),
                  "has_mask_e": attention_mask is not None, "stream": stream, "lm_factor": float(lm_factor),
                  "has_lm": bool(has_lm), "with_heads": bool(with_heads)}
             a["ids_e"] = torch.empty(B * Se, dtype=torch.int64, device=dev)
@@ -672,18 +720,23 @@ class Engine:
             a["pad_d"] = a["pad_d_bool"].view(torch.uint8)
             a["labels"] = torch.full((max(B * Sd, 1),), -100, dtype=torch.int64, device=dev)
             a["feat_ptrs"] = torch.zeros(B, dtype=torch.int64, device=dev)
-            a["feat_ptrs_host"] = torch.zeros(B, dtype=torch.int64).pin_memory()
+            a["feat_ptrs_host"] = [torch.zeros(B, dtype=torch.int64).pin_memory() for _ in range(2)]
             a["row_off"] = torch.zeros(B + 1, dtype=torch.int32, device=dev)
-            a["row_off_host"] = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
-            a["packed_buf"] = torch.empty(max(R, 1), self.fin, dtype=F32, device=dev) if packed else None
+            a["row_off_host"] = [torch.zeros(B + 1, dtype=torch.int32).pin_memory() for _ in range(2)]
+            a["stage_ev"] = [None, None]
+            a["packed_buf"] = torch.zeros(max(cap, 1), self.fin, dtype=F32, device=dev) if packed else None
             a["packed"] = a["packed_buf"]
             a["loss"] = torch.zeros(1, dtype=F32, device=dev)
+            a["seed"] = torch.zeros(1, dtype=torch.int64, device=dev)
+            a["serial"] = 0
             a["flb"] = None
-            self.arenas[key] = a
+            self.remember(key, a)
+        else:
+            self.touch(key)
         off = [0]
         for c in counts:
             off.append(off[-1] + c)
-        a["row_off_host"].copy_(torch.tensor(off, dtype=torch.int32))
+        a["row_off_list"] = off
         return a, key
 
     # ------------------------------------------------------------------ public: training step pieces
@@ -700,6 +753,9 @@ class Engine:
             plans = {"fwd": self._build_train_fwd(a), "flb": a["flb"].data_ptr()}
             self.plans[key] = plans
         a["heads_ctx"] = None
+        self._fwd_serial += 1
+        a["serial"] = self._fwd_serial       # stamps the activation stash: a later forward on this workspace overwrites it
+        a["__plans"] = plans
         plans["fwd"].run()
         self.last_train = (a, key)
         self.launches_last = plans["fwd"].kernel_count()
@@ -711,12 +767,18 @@ class Engine:
         base, end = self.store.G.data_ptr(), self.store.G.data_ptr() + 4 * self.store.total
         return any(p.grad is not None and base <= p.grad.data_ptr() < end for p in self.store.params.values())
 
-    def train_backward(self, a, key, upstream, accumulate):
+    def train_backward(self, a, key, upstream, accumulate, serial=None):
+        if serial is not None and a["serial"] != serial:
+            raise RuntimeError(
+                "backward through a KM-BART training forward whose activation stash has been overwritten: another training-mode "
+                "forward with the same input shape ran on this model before this loss was back-propagated (the fused step keeps "
+                "ONE stash per shape).  Call backward() before the next forward of the same shape, or sum the losses of "
+                "different-shape micro-batches instead.")
         if upstream is not None:
             self.upstream.copy_(upstream.reshape(1).to(F32))
         else:
             self.upstream.fill_(1.0)
-        plans = self.plans[key]
+        plans = a["__plans"]       # survives an LRU eviction of the workspace between forward and backward
         if a.get("heads_ctx"):
             from .heads import heads_backward
             heads_backward(self, a, a["heads_ctx"], accumulate)

@@ -101,7 +101,11 @@ def heads_backward(eng, a, ctx, accumulate):
 class _PretrainStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, owner, arena, key, *params):
-        ctx.owner, ctx.arena, ctx.key, ctx.n_params = owner, arena, key, len(params)
+        ctx.owner, ctx.arena, ctx.key, ctx.n_params, ctx.serial = owner, arena, key, len(params), arena["serial"]
+        hc = arena.get("heads_ctx")
+        # heads that took no part in this batch get grad None, like plain autograd in the reference (HF AdamW then skips
+        # them: no momentum step, no step-count increment) instead of a zero gradient
+        ctx.active_heads = {x["loss_name"].replace("_loss", "_head") for x in hc["heads"]} if hc else set()
         return arena["loss"].clone().squeeze(0)
 
     @staticmethod
@@ -109,11 +113,16 @@ class _PretrainStep(torch.autograd.Function):
         owner = ctx.owner
         eng = owner._engine()
         accumulate = eng.grads_alias_flat_buffer()
-        eng.train_backward(ctx.arena, ctx.key, grad_loss, accumulate)
+        eng.train_backward(ctx.arena, ctx.key, grad_loss, accumulate, serial=ctx.serial)
         if accumulate:
             return (None, None, None) + (None,) * ctx.n_params
         store = eng.store
-        return (None, None, None) + tuple(store.grad_view(n) if p.requires_grad else None for n, p in owner._named_params_cache)
+
+        def inactive(n):
+            top = n.split(".", 1)[0]
+            return top.endswith("_head") and top not in ctx.active_heads
+        return (None, None, None) + tuple(store.grad_view(n) if (p.requires_grad and not inactive(n)) else None
+                                          for n, p in owner._named_params_cache)
 
 
 def pretraining_forward(model, input_ids, image_features, attention_mask, decoder_input_ids, decoder_attention_mask, labels,

@@ -68,7 +68,7 @@ class _FusedTrainStep(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, owner, arena, key, *params):
-        ctx.owner, ctx.arena, ctx.key = owner, arena, key
+        ctx.owner, ctx.arena, ctx.key, ctx.serial = owner, arena, key, arena["serial"]
         ctx.n_params = len(params)
         return arena["loss"].clone().squeeze(0)
 
@@ -79,7 +79,7 @@ class _FusedTrainStep(torch.autograd.Function):
         # decided here, not at forward time: the reference's loop calls optimizer.zero_grad() between
         # forward and backward (src/training.py:134-142)
         accumulate = eng.grads_alias_flat_buffer()
-        eng.train_backward(ctx.arena, ctx.key, grad_loss, accumulate)
+        eng.train_backward(ctx.arena, ctx.key, grad_loss, accumulate, serial=ctx.serial)
         store = eng.store
         if accumulate:
             # gradients were added in place into the buffer the existing .grad tensors alias

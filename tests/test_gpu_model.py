@@ -709,3 +709,74 @@ def test_split_optimizer_step_with_deferred_tail_matches_single_launch(fwd_setup
         finals.append([p_.detach().clone() for p_ in model.parameters()])
     for a_, b_ in zip(*finals):
         assert torch.equal(a_, b_)
+
+
+# ------------------------------------------------------------------ workspace management (arenas keyed on exact shapes)
+def test_region_count_is_a_capacity_and_workspaces_are_bounded(fwd_setup, monkeypatch):
+    """The reference's batches change shape every step (collator pads to the longest sequence, 10-50 RoIs per image):
+    the number of regions is a capacity of the workspace (rows past it stay zero), and at most KMBART_MAX_ARENAS
+    workspaces stay resident."""
+    ocfg, sd, _, _ = fwd_setup
+    monkeypatch.setenv("KMBART_MAX_ARENAS", "3")
+    model = make_model(ocfg, sd, train=True)
+    eng = model._engine()
+    assert eng.max_arenas == 3
+    big = O.synthetic_batch(ocfg, batch=4, n_regions=9, n_ctx=14, tgt_len=10, seed=21)
+    small = O.synthetic_batch(ocfg, batch=4, n_regions=9, n_ctx=14, tgt_len=10, seed=22)
+    for b in range(4):      # fewer regions in the second batch, same padded lengths: <img_feat> slots become plain tokens
+        keep = 9 - 2 * b
+        small["image_features"][b] = small["image_features"][b][:keep]
+        row = small["input_ids"][b]
+        slots = (row == ocfg.img_feat_id).nonzero().flatten()
+        row[slots[keep:]] = 17
+    for batch in (big, small, big, small):
+        osd = {k: v.clone().requires_grad_(k != "final_logits_bias") for k, v in sd.items()}
+        lo, _, _, _ = O.forward_conditional_generation(osd, ocfg, **batch)
+        lo.backward()
+        model.zero_grad()
+        loss = model(**to_cuda_batch(batch))[0]
+        loss.backward()
+        assert abs(loss.item() - lo.item()) <= 1e-2 * lo.item()
+        name = "model.encoder.embed_images.linear.weight"
+        assert rel_err(dict(model.named_parameters())[name].grad, osd[name].grad) <= 3e-2
+    train_keys = [k for k in eng.arenas if k[0] == "train"]
+    assert len(train_keys) == 1, train_keys          # one workspace served both region counts
+    for n_ctx in (10, 11, 12, 13, 15, 16):           # six more shapes: the bound holds
+        b = O.synthetic_batch(ocfg, batch=2, n_regions=3, n_ctx=n_ctx, tgt_len=6, seed=n_ctx)
+        model(**to_cuda_batch(b))[0].backward()
+    assert len(eng.arenas) <= 3 and len(eng.plans) <= 3
+
+
+def test_backward_after_the_stash_was_overwritten_raises_and_other_shapes_do_not_interfere(fwd_setup):
+    """Plain autograd (the reference) keeps every forward's graph; the fused step keeps one activation stash per shape.
+    A second same-shape forward before backward must fail loudly, a different-shape forward in between must not change
+    the first loss's gradients (its dropout seed lives in its own workspace)."""
+    ocfg, sd, batch, _ = fwd_setup
+    model = make_model(ocfg, sd, train=True)
+    model.config.dropout = 0.1
+    model._eng = None                      # rebuild the engine with dropout on
+    cb = to_cuda_batch(batch)
+    other = to_cuda_batch(O.synthetic_batch(ocfg, batch=2, n_regions=3, n_ctx=9, tgt_len=5, seed=5))
+    torch.manual_seed(1)
+    model = make_model(ocfg, sd, train=True)
+    model.config.dropout = 0.1
+    l1 = model(**cb)[0]
+    l2 = model(**cb)[0]
+    with pytest.raises(RuntimeError, match="overwritten"):
+        l1.backward()
+    model.zero_grad()
+    l2.backward()                          # the latest forward of the shape is fine
+    # a different shape between forward and backward: same gradients as without it
+    def grads_with(interleave):
+        torch.manual_seed(7)
+        m = make_model(ocfg, sd, train=True)
+        m.config.dropout = 0.1
+        m._engine().seed_state.fill_(12345)
+        la = m(**cb)[0]
+        if interleave:
+            m(**other)[0]
+        la.backward()
+        return {n: p.grad.clone() for n, p in m.named_parameters()}
+    ga, gb = grads_with(False), grads_with(True)
+    for n in ga:     # atomically accumulated gradients (embedding scatter) are not bit-reproducible; a different mask would be gross
+        assert torch.allclose(ga[n], gb[n], rtol=1e-3, atol=1e-6), n
