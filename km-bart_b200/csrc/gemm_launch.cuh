@@ -5,6 +5,10 @@
 
 namespace kmb {
 
+// SMs the persistent GEMM grids (and the tile / split-K cost models) plan for.  KMBART_GEMM_SMS caps it: under data
+// parallelism NCCL's all-reduce CTAs occupy a few SMs while the backward GEMMs run; a statically scheduled persistent grid
+// that assumes all 148 then has CTA pairs that cannot be resident and run as a second wave (kmbart/parallel.py sets the cap
+// together with NCCL_MAX_CTAS).
 inline int gemm_num_sms() {
   static int n = 0;
   if (!n) {
@@ -12,6 +16,8 @@ inline int gemm_num_sms() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    const char* e = getenv("KMBART_GEMM_SMS");
+    if (e && atoi(e) >= 2 && atoi(e) < n) n = atoi(e) & ~1;
   }
   return n;
 }

@@ -411,5 +411,7 @@ def get_session(eng, B, Se, rows, max_len, has_pad):
     s = eng.arenas.get(key)
     if s is None:
         s = DecodeSession(eng, B, Se, rows, max_len, has_pad)
-        eng.arenas[key] = s
+        eng.remember(key, s)      # least-recently-used bound shared with the training workspaces (a session holds its graphs)
+    else:
+        eng.touch(key)
     return s

@@ -535,8 +535,8 @@ class Engine:
         Me, Md = B * Se, B * Sd
         a["Me"], a["Md"] = Me, Md
         p_drop = float(cfg.dropout) if a["training"] else 0.0
-        assert float(cfg.attention_dropout) == 0.0 or not a["training"], "attention_dropout > 0 is not supported"
-        assert float(cfg.activation_dropout) == 0.0 or not a["training"], "activation_dropout > 0 is not supported"
+        if a["training"] and (float(cfg.attention_dropout) > 0.0 or float(cfg.activation_dropout) > 0.0):
+            raise ValueError("attention_dropout / activation_dropout > 0 are not implemented by the B200 kernels (only `dropout` is)")
         fwd = Plan()
         fwd.stream = a["stream"]
         # the dropout seed of a step lives in ITS workspace: a forward on another shape between this forward and its

@@ -358,6 +358,12 @@ class GenerationMixin:
                               top_k, top_p, repetition_penalty, no_repeat_ngram_size, bad_words_ids, pad_token_id,
                               eos_token_id, batch_size, num_return_sequences, length_penalty, num_beams, vocab_size,
                               encoder_outputs, attention_mask, use_cache, model_specific_kwargs, sess=None):
+        if (sess is None and not do_sample and repetition_penalty == 1.0 and no_repeat_ngram_size == 0 and bad_words_ids is None
+                and max_length > 2 and cur_len == 1 and input_ids.is_cuda and getattr(self, "_device_controller", True)
+                and self._select_kernels_fit(num_beams)):
+            return self._beam_search_device_controller(input_ids, max_length, min_length, early_stopping, pad_token_id, eos_token_id,
+                                                       batch_size, num_return_sequences, length_penalty, num_beams, vocab_size,
+                                                       encoder_outputs, attention_mask, use_cache, model_specific_kwargs)
         generated_hyps = [BeamHypotheses(num_beams, max_length, length_penalty, early_stopping=early_stopping)
                           for _ in range(batch_size)]
         beam_scores = torch.zeros((batch_size, num_beams), dtype=torch.float, device=input_ids.device)
@@ -470,6 +476,46 @@ class GenerationMixin:
         else:
             decoded = torch.stack(best).type(torch.long).to(next(self.parameters()).device)
         return decoded
+
+    def _beam_search_device_controller(self, input_ids, max_length, min_length, early_stopping, pad_token_id, eos_token_id, batch_size,
+                                       num_return_sequences, length_penalty, num_beams, vocab_size, encoder_outputs, attention_mask,
+                                       use_cache, model_specific_kwargs):
+        """_generate_beam_search with the model called eagerly (legacy cache dicts, or the fp32 parity mode) and the loop body
+        — log_softmax, forced tokens, top 2 * num_beams, hypothesis bookkeeping, beam re-ordering — on the device
+        (kmbart.decode.BeamController): the only host synchronisation is an "all done" poll every fourth step."""
+        from kmbart.decode import BeamController
+        from kmbart import lib as L
+        cfg = self.config
+        dev = input_ids.device
+        key = (batch_size, num_beams, max_length, eos_token_id, pad_token_id, bool(early_stopping), float(length_penalty), dev)
+        cache = self.__dict__.setdefault("_beam_controllers", {})
+        ctl = cache.get(key)
+        if ctl is None:
+            cache.clear()      # one resident controller is enough for this path
+            ctl = cache[key] = BeamController(dev, batch_size, num_beams, vocab_size, max_length, eos_token_id, pad_token_id,
+                                              early_stopping, length_penalty)
+        ctl.reset(int(input_ids[0, 0].item()))
+        lib = L.load()
+        past = (encoder_outputs, None) if encoder_outputs is not None else None
+        cur_len = 1
+        while cur_len < max_length:
+            dec_ids = ctl.hist[:, :cur_len].long()
+            model_inputs = self.prepare_inputs_for_generation(dec_ids, past=past, attention_mask=attention_mask, use_cache=use_cache,
+                                                              **model_specific_kwargs)
+            outputs = self(**model_inputs)
+            logits = outputs[0][:, -1, :].float().contiguous()
+            if self._use_cache(outputs, use_cache):
+                past = outputs[1]
+            force = cfg.bos_token_id if cur_len == 1 else (cfg.eos_token_id if (cur_len == max_length - 1 and cfg.eos_token_id is not None) else -1)
+            ban = int(eos_token_id is not None and cur_len < min_length)
+            ctl.step(lib, logits, cur_len, int(force), ban, torch.cuda.current_stream(dev).cuda_stream)
+            step_no = cur_len
+            cur_len += 1
+            if eos_token_id is not None and step_no % 4 == 0 and cur_len < max_length and ctl.all_done():
+                break
+            if past is not None and past[1] is not None:
+                past = self._reorder_cache(past, ctl.beam_idx.long())
+        return ctl.finalize(BeamHypotheses, cur_len, num_return_sequences, max_length)
 
     # ------------------------------------------------------------------ reference hooks (src/model/mixins.py:386-434)
     def prepare_inputs_for_generation(self, decoder_input_ids, past, attention_mask, use_cache, **kwargs):

@@ -116,6 +116,18 @@ class PretrainedBartModel(nn.Module):
         self.apply(self._init_weights)
         self.tie_weights()
 
+    def train(self, mode=True):
+        """The fused kernels implement `dropout` (embeddings, residual branches) but neither dropout on the attention
+        probabilities nor on the FFN activation (vcg_train.py:78-83 exposes both as flags): refuse to TRAIN with them
+        here, when the script switches to training mode, instead of computing a different model."""
+        cfg = getattr(self, "config", None)
+        if mode and cfg is not None:
+            for knob in ("attention_dropout", "activation_dropout"):
+                if float(getattr(cfg, knob, 0.0) or 0.0) > 0.0:
+                    raise ValueError(f"config.{knob} = {getattr(cfg, knob)} is not implemented by the B200 kernels (only `dropout` is); "
+                                     f"set it to 0 for training — inference ignores it")
+        return super().train(mode)
+
     def tie_weights(self):
         pass  # embeddings are tied by construction (one nn.Embedding object shared by encoder and decoder)
 

@@ -780,3 +780,81 @@ def test_backward_after_the_stash_was_overwritten_raises_and_other_shapes_do_not
     ga, gb = grads_with(False), grads_with(True)
     for n in ga:     # atomically accumulated gradients (embedding scatter) are not bit-reproducible; a different mask would be gross
         assert torch.allclose(ga[n], gb[n], rtol=1e-3, atol=1e-6), n
+
+
+# ------------------------------------------------------------------ optimizer side-car (src/utils.py:20-39 training_data.pt)
+def test_optimizer_state_round_trips_through_the_reference_training_data_layout(fwd_setup, tmp_path):
+    """save_training_data / load_training_data of the reference (src/utils.py:20-39) store optimizer.state_dict() next to
+    the model: the fused AdamW keeps the HF-3.0.2 layout ({'step','exp_avg','exp_avg_sq'} per parameter index in
+    parameters() order, param_groups with correct_bias), resumes bit-for-bit from it, and accepts a state dict written by
+    the HF-3.0.2 optimizer itself (oracle/hf302_shim.AdamW)."""
+    from kmbart.optim import AdamW
+    from oracle import hf302_shim as S
+    ocfg, sd, batch, _ = fwd_setup
+    cb = to_cuda_batch(batch)
+    hyper = dict(lr=1e-3, weight_decay=0.01)
+
+    def run_steps(model, opt, n, grads_out=None):
+        for _ in range(n):
+            loss = model(**cb)[0]
+            opt.zero_grad()
+            loss.backward()
+            if grads_out is not None:
+                grads_out.append([p.grad.detach().cpu().clone() for p in model.parameters()])
+            opt.step()
+
+    model = make_model(ocfg, sd, train=True)
+    opt = AdamW(model.parameters(), **hyper)
+    grads = []
+    p0 = [p.detach().cpu().clone() for p in model.parameters()]
+    run_steps(model, opt, 2, grads)
+    # --- layout
+    st = opt.state_dict()
+    n = len(list(model.parameters()))
+    assert st["param_groups"][0]["params"] == list(range(n))
+    assert {"lr", "betas", "eps", "weight_decay", "correct_bias"} <= set(st["param_groups"][0])
+    assert set(st["state"]) == set(range(n)) and set(st["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and st["state"][0]["step"] == 2
+    # --- same two steps with the HF-3.0.2 optimizer on the host, fed the same gradients: same moments, same weights
+    host = [torch.nn.Parameter(t.clone()) for t in p0]
+    hf = S.AdamW(host, **hyper)
+    for g in grads:
+        for p, gi in zip(host, g):
+            p.grad = gi.clone()
+        hf.step()
+    hst = hf.state_dict()
+    for i, p in enumerate(model.parameters()):
+        assert torch.allclose(st["state"][i]["exp_avg"].cpu(), hst["state"][i]["exp_avg"], rtol=1e-5, atol=1e-9), i
+        assert torch.allclose(st["state"][i]["exp_avg_sq"].cpu(), hst["state"][i]["exp_avg_sq"], rtol=1e-5, atol=1e-12), i
+        assert torch.allclose(p.detach().cpu(), host[i].detach(), rtol=1e-5, atol=1e-7), i
+    # --- save in the reference's side-car format, resume in a fresh process-like state
+    torch.save({"optimizer": st, "scaler": None, "epoch": 3}, tmp_path / "training_data.pt")
+    weights = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    run_steps(model, opt, 1)
+    cont = [p.detach().clone() for p in model.parameters()]
+    for source in ("own", "hf"):
+        m2 = make_model(ocfg, sd, train=True)
+        m2.load_state_dict(weights)
+        o2 = AdamW(m2.parameters(), **hyper)
+        ck = torch.load(tmp_path / "training_data.pt", map_location="cuda")
+        o2.load_state_dict(ck["optimizer"] if source == "own" else hst)
+        assert ck["epoch"] == 3
+        run_steps(m2, o2, 1)
+        for i, (a, b) in enumerate(zip(cont, m2.parameters())):
+            assert torch.allclose(a, b.detach(), rtol=1e-4, atol=1e-6), (source, i)
+
+
+def test_training_dropout_knobs_the_kernels_do_not_implement_fail_at_train_time_not_mid_step(fwd_setup):
+    """vcg_train.py:78-83 exposes --attention_dropout / --activation_dropout; the fused kernels implement `dropout` only:
+    switching such a model to training mode raises a ValueError that names the knob (inference with it is fine)."""
+    ocfg, sd, batch, _ = fwd_setup
+    from src.model.model import MultiModalBartForConditionalGeneration
+    cfg = product_config(ocfg)
+    cfg.attention_dropout = 0.1
+    model = MultiModalBartForConditionalGeneration(cfg)
+    load_oracle_weights(model, sd)
+    model.cuda().eval()
+    with torch.no_grad():
+        loss = model(**to_cuda_batch(batch))[0]
+    assert torch.isfinite(loss)
+    with pytest.raises(ValueError, match="attention_dropout"):
+        model.train()
