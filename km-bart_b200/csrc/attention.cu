@@ -1045,6 +1045,18 @@ static void token_major_strides(kmb::AttnParams& p) {
   p.sbo = (int64_t)p.Sq * p.ldo; p.sho = kmb::DH;
 }
 
+namespace kmb {   // attention_tc05.cu
+bool attn_tc05_enabled(int is_bwd, int Sq, int Sk);
+int attn_fwd_tc05(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* o, int64_t ldo, float* lse,
+                  const uint8_t* key_pad, int B, int H, int Sq, int Sk, int causal, float scale, cudaStream_t st);
+int attn_bwd_tc05(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, const void* o, int64_t ldo, const void* d_o,
+                  int64_t lddo, const float* lse, const uint8_t* key_pad, void* dq, void* dk, void* dv, int64_t lddq, int64_t lddk, int64_t lddv,
+                  int B, int H, int Sq, int Sk, int causal, float scale, cudaStream_t st);
+static bool tc05_aligned(const void* a, const void* b, const void* c, int64_t la, int64_t lb, int64_t lc) {
+  return !(((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) && !((la | lb | lc) % 8);
+}
+}  // namespace kmb
+
 extern "C" int kmb_attn_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
                             void* o, int64_t ldo, float* lse, const uint8_t* key_pad, int B, int H, int Sq, int Sk,
                             int head_dim, int causal, float scale, kmb_stream_t stream) {
@@ -1058,6 +1070,10 @@ extern "C" int kmb_attn_fwd(const void* q, const void* k, const void* v, int64_t
     kmb_set_last_error("kmb_attn_fwd: bad argument (head_dim must be 64, strides multiples of 8)", __FILE__, __LINE__);
     return KMB_ERR_ARG;
   }
+  // every attention of the base model (S <= 128) is one tcgen05 tile per (batch, head): attention_tc05.cu
+  if (Sq <= 128 && Sk <= 128 && attn_tc05_enabled(0, Sq, Sk) && !attn_fwd_persist_enabled() && tc05_aligned(q, k, v, ldq, ldk, ldv) &&
+      !((uintptr_t)o & 15))
+    return attn_fwd_tc05(q, k, v, ldq, ldk, ldv, o, ldo, lse, key_pad, B, H, Sq, Sk, causal, scale, (cudaStream_t)stream);
   if (set_attn_smem_attrs()) return KMB_ERR_CUDA;
   if (Sq <= 128 && Sk <= 128 && scale > 0.f && attn_fwd_persist_enabled()) {
     const int SqP = (Sq + 15) & ~15, SkP = (Sk + 15) & ~15;
@@ -1129,6 +1145,9 @@ extern "C" int kmb_attn_bwd(const void* q, const void* k, const void* v, int64_t
     return KMB_ERR_ARG;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (Sq <= 128 && Sk <= 128 && attn_tc05_enabled(1, Sq, Sk) && attn_bwd_fused_enabled() && tc05_aligned(q, k, v, ldq, ldk, ldv) &&
+      tc05_aligned(d_o, o, dq, lddo, ldo, lddq) && tc05_aligned(dk, dv, dq, lddk, lddv, lddq))
+    return attn_bwd_tc05(q, k, v, ldq, ldk, ldv, o, ldo, d_o, lddo, lse, key_pad, dq, dk, dv, lddq, lddk, lddv, B, H, Sq, Sk, causal, scale, st);
   if (Sq <= FB_MAXS && Sk <= FB_MAXS && attn_bwd_fused_enabled()) {
     const int SqP = (Sq + 15) & ~15, SkP = (Sk + 15) & ~15;
     static bool attr_set = false;

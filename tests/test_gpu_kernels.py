@@ -239,12 +239,14 @@ def ref_attention(q, k, v, pad, causal, scale):
 @pytest.mark.parametrize("B,H,Sq,Sk,causal,use_pad", [(3, 2, 100, 100, 0, 1), (2, 12, 48, 48, 1, 1), (2, 3, 48, 100, 0, 1),
                                                       (1, 2, 7, 7, 1, 0), (2, 2, 130, 130, 1, 0), (2, 2, 86, 200, 0, 1),
                                                       (40, 12, 128, 128, 1, 1), (2, 4, 17, 33, 0, 1), (30, 12, 100, 100, 0, 1)])
-@pytest.mark.parametrize("persist,split", [(0, 0), (1, 0), (0, 1)])
-def test_attention_forward_backward(lib, monkeypatch, B, H, Sq, Sk, causal, use_pad, persist, split):
-    """split = 1 forces the three-kernel backward (0: fused persistent backward when Sq, Sk <= 128);
-    persist = 1 takes the opt-in persistent forward instead of the tiled one (the product default is (0, 0))"""
+@pytest.mark.parametrize("persist,split,tc05", [(0, 0, 1), (0, 0, 0), (1, 0, 0), (0, 1, 0)])
+def test_attention_forward_backward(lib, monkeypatch, B, H, Sq, Sk, causal, use_pad, persist, split, tc05):
+    """tc05 = 1: the tcgen05 / TMEM kernels of attention_tc05.cu for every Sq, Sk <= 128 (the product default takes them where
+    they are faster: the backward of encoder-sized tiles); tc05 = 0: the mma.sync kernels (which longer sequences always use) — split = 1 forces their three-kernel backward (0: fused persistent
+    backward when Sq, Sk <= 128), persist = 1 their opt-in persistent forward instead of the tiled one"""
     monkeypatch.setenv("KMBART_ATTN_BWD_SPLIT", str(split))
     monkeypatch.setenv("KMBART_ATTN_FWD_PERSIST", str(persist))
+    monkeypatch.setenv("KMBART_ATTN_TC05", str(tc05))
     L = lib.load()
     d = H * 64
     q, k, v = rnd(B * Sq, d, seed=1), rnd(B * Sk, d, seed=2), rnd(B * Sk, d, seed=3)
