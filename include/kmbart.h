@@ -151,13 +151,14 @@ int kmb_attn_f32(const float* q, int64_t q_row_stride, const float* k, const flo
 int kmb_greedy_select(const float* logits, int64_t ld, int rows, int V, int eos_token_id, int pad_token_id,
                       int ban_eos, int cur_len, int64_t* unfinished, int64_t* sent_len, int64_t* out_tokens,
                       int64_t out_ld, int64_t* ids_next, kmb_stream_t stream);
-/* Top-k sampling step of the no-beam loop, on device: temperature, top-k filter (0 = none; ties with the k-th value
- * survive), softmax, one multinomial draw per row from hash(seed[0], row, cur_len), then the same bookkeeping as
+/* Sampling step of the no-beam loop, on device: temperature, top-k filter (0 = none; ties with the k-th value survive),
+ * nucleus (top-p) filter on the renormalised softmax (1.0 = none; keep a token iff the mass sorted strictly before it is <=
+ * top_p), one multinomial draw per row from hash(seed[0], row, cur_len), then the same bookkeeping as
  * kmb_greedy_select.  One CTA per row holds the logits row in shared memory (V <= kmb_select_max_vocab()).
  * replaces: HF-3.0.2 _generate_no_beam_search do_sample branch (top_k_top_p_filtering + softmax + multinomial) reached
  *   from src/model/mixins.py:368-382 with the vcg_generate.py defaults (src/generation.py:22-32). */
 int kmb_select_max_vocab(void);
-int kmb_sample_select(const float* logits, int64_t ld, int rows, int V, float temperature, int top_k, int eos_token_id,
+int kmb_sample_select(const float* logits, int64_t ld, int rows, int V, float temperature, int top_k, float top_p, int eos_token_id,
                       int pad_token_id, int ban_eos, int cur_len, const uint64_t* seed, int64_t* unfinished,
                       int64_t* sent_len, int64_t* out_tokens, int64_t out_ld, int64_t* ids_next, kmb_stream_t stream);
 /* Beam-search step on device (num_beams > 1, do_sample = False): log_softmax of the (optionally forced) logits, EOS ban

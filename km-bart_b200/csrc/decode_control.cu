@@ -98,8 +98,67 @@ __device__ uint32_t dc_radix_kth(const float* x, int V, int k, DcScratch& s) {
   return prefix;
 }
 
-// ------------------------------------------------------------------ top-k sampling (num_beams == 1, do_sample)
-__global__ void __launch_bounds__(DC_THREADS) sample_select_kernel(const float* logits, int64_t ld, int V, float inv_temp, int top_k, int eos, int pad,
+// Nucleus threshold on the (already top-k filtered, exponentiated) row e[0, V): HF-3.0.2 top_k_top_p_filtering keeps a token
+// iff the probability mass of the tokens sorted strictly before it is <= top_p (the first token always survives).  With
+// G(x) = mass of entries > x that is "keep iff G(e_i) <= top_p * total": returns the key of the smallest kept value, found by
+// the same 4 x 8-bit radix descent with per-bin MASS histograms (e >= 0, so the float bit pattern orders like the value).
+__device__ uint32_t dc_radix_mass(const float* e, int V, float limit, DcScratch& s) {
+  const int lane = threadIdx.x & 31;
+  float* fh = reinterpret_cast<float*>(s.hist);
+  uint32_t prefix = 0, mask = 0;
+  float above = 0.f;                         // mass of the bins already known to lie above the threshold
+  const int Vp = (V + 31) & ~31;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += DC_THREADS) fh[i] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < Vp; i += DC_THREADS) {
+      const float v = i < V ? e[i] : 0.f;
+      const uint32_t key = __float_as_uint(v);
+      const bool in = i < V && v > 0.f && (key & mask) == prefix;
+      const unsigned act = __ballot_sync(0xffffffffu, in);
+      if (in) {
+        const uint32_t bin = (key >> shift) & 255u;
+        const unsigned peers = __match_any_sync(act, bin);
+        float acc = 0.f;                     // mass of the lanes that share this bin, summed in lane order
+        for (unsigned q = peers; q; q &= q - 1) acc += __shfl_sync(peers, v, __ffs(q) - 1);
+        if (lane == __ffs(peers) - 1) atomicAdd(&fh[bin], acc);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {   // bins from the top, 8 per lane: first bin whose inclusive mass exceeds the limit
+      float c[8], tot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = fh[255 - (lane * 8 + j)]; tot += c[j]; }
+      float incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      float cum = above + incl - tot;
+      const bool mine = cum <= limit && above + incl > limit;
+      const unsigned who = __ballot_sync(0xffffffffu, mine);
+      if (who == 0) {                         // rounding: everything fits under the limit -> lowest populated bin
+        if (lane == 0) { s.bc[0] = 0; s.bc[2] = __float_as_uint(above + __shfl_sync(0xffffffffu, incl, 31)); }
+      } else if (lane == __ffs(who) - 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (cum + c[j] > limit) { s.bc[0] = 255 - (lane * 8 + j); s.bc[2] = __float_as_uint(cum); break; }
+          cum += c[j];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= s.bc[0] << shift;
+    mask |= 255u << shift;
+    above = __uint_as_float(s.bc[2]);
+    __syncthreads();
+  }
+  return prefix;
+}
+
+// ------------------------------------------------------------------ top-k / top-p sampling (num_beams == 1, do_sample)
+__global__ void __launch_bounds__(DC_THREADS) sample_select_kernel(const float* logits, int64_t ld, int V, float inv_temp, int top_k, float top_p, int eos, int pad,
                                                                   int ban_eos, int cur_len, const unsigned long long* seed, int64_t* unfinished,
                                                                   int64_t* sent_len, int64_t* out, int64_t out_ld, int64_t* ids_next) {
   extern __shared__ __align__(16) uint8_t dc_smem[];
@@ -133,8 +192,22 @@ __global__ void __launch_bounds__(DC_THREADS) sample_select_kernel(const float* 
     loc += e;
     if (keep) last_kept = i;
   }
-  // exclusive scan of the chunk sums over the 1024 threads (fixed order)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (top_p < 1.0f) {
+    // nucleus filter on the surviving probabilities (HF applies it after the top-k filter, on the renormalised softmax)
+    const float tot0 = dc_block_sum(loc, sc);
+    __syncthreads();
+    const uint32_t pthr = dc_radix_mass(xs, V, top_p * tot0, sc);
+    loc = 0.f;
+    last_kept = -1;
+    for (int i = i0; i < i1; ++i) {
+      const float e = xs[i];
+      const bool keep = e > 0.f && __float_as_uint(e) >= pthr;
+      if (!keep) xs[i] = 0.f;
+      else { loc += e; last_kept = i; }
+    }
+  }
+  // exclusive scan of the chunk sums over the 1024 threads (fixed order)
   float incl = loc;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -368,10 +441,10 @@ static int dc_row_smem(int V) { return (int)((((size_t)V * 4 + 15) & ~(size_t)15
 
 extern "C" int kmb_select_max_vocab(void) { return (DC_MAX_DYN_SMEM - (int)sizeof(kmb::DcScratch) - 128) / 4; }
 
-extern "C" int kmb_sample_select(const float* logits, int64_t ld, int rows, int V, float temperature, int top_k, int eos_token_id,
+extern "C" int kmb_sample_select(const float* logits, int64_t ld, int rows, int V, float temperature, int top_k, float top_p, int eos_token_id,
                                  int pad_token_id, int ban_eos, int cur_len, const uint64_t* seed, int64_t* unfinished, int64_t* sent_len,
                                  int64_t* out_tokens, int64_t out_ld, int64_t* ids_next, kmb_stream_t stream) {
-  if (!logits || rows <= 0 || V <= 0 || V > kmb_select_max_vocab() || !(temperature > 0.f) || top_k < 0 || !seed || !unfinished || !sent_len ||
+  if (!logits || rows <= 0 || V <= 0 || V > kmb_select_max_vocab() || !(temperature > 0.f) || top_k < 0 || !(top_p >= 0.f) || !seed || !unfinished || !sent_len ||
       !out_tokens || !ids_next || cur_len < 0 || cur_len >= out_ld) {
     kmb_set_last_error("kmb_sample_select: bad argument (vocabulary must fit one CTA's shared memory)", __FILE__, __LINE__);
     return KMB_ERR_ARG;
@@ -385,7 +458,7 @@ extern "C" int kmb_sample_select(const float* logits, int64_t ld, int rows, int 
     attr = true;
   }
   kmb::sample_select_kernel<<<rows, kmb::DC_THREADS, dc_row_smem(V), (cudaStream_t)stream>>>(
-      logits, ld, V, 1.0f / temperature, top_k, eos_token_id, pad_token_id, ban_eos, cur_len, (const unsigned long long*)seed, unfinished, sent_len,
+      logits, ld, V, 1.0f / temperature, top_k, top_p, eos_token_id, pad_token_id, ban_eos, cur_len, (const unsigned long long*)seed, unfinished, sent_len,
       out_tokens, out_ld, ids_next);
   KMB_CHECK_LAUNCH();
   return KMB_OK;

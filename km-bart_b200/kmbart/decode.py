@@ -321,7 +321,8 @@ class DecodeSession:
         eos = -1 if sel["eos"] is None else int(sel["eos"])
         pad_id = 0 if sel["pad"] is None else int(sel["pad"])
         L.check(self.eng.lib.kmb_sample_select(logits.data_ptr(), logits.shape[1], self.rows, logits.shape[1], float(sel["temperature"]),
-                                               int(sel["top_k"]), eos, pad_id, int(eos >= 0 and cur_len < sel["min_length"]), cur_len,
+                                               int(sel["top_k"]), float(sel.get("top_p", 1.0)), eos, pad_id,
+                                               int(eos >= 0 and cur_len < sel["min_length"]), cur_len,
                                                self.seed.data_ptr(), self.unfinished.data_ptr(), self.sent_len.data_ptr(), self.out.data_ptr(),
                                                self.max_len, self.ids.data_ptr(), torch.cuda.current_stream(self.eng.device).cuda_stream),
                 "kmb_sample_select")

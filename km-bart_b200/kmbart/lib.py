@@ -93,7 +93,7 @@ _PROTOS = {
     "kmb_greedy_select": [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                           c_void_p, c_void_p],
     "kmb_select_max_vocab": [],
-    "kmb_sample_select": [c_void_p, c_int64, c_int, c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+    "kmb_sample_select": [c_void_p, c_int64, c_int, c_int, c_float, c_int, c_float, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                           c_void_p, c_int64, c_void_p, c_void_p],
     "kmb_beam_step": [c_void_p, c_int64, C.POINTER(BeamState), c_int, c_int, c_int, c_void_p],
     "kmb_attn_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,

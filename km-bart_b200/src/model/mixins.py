@@ -182,13 +182,13 @@ class GenerationMixin:
         # Same token semantics as the legacy loops below; knobs the decode chain does not implement fall through.
         fast_ok = (use_cache and repetition_penalty == 1.0 and no_repeat_ngram_size == 0 and bad_words_ids is None
                    and not model_specific_kwargs and max_length <= 256 and input_ids.shape[1] <= 256
-                   and ((num_beams == 1 and (not do_sample or top_p == 1.0)) or (num_beams > 1 and not do_sample and max_length > 2))
+                   and (num_beams == 1 or (not do_sample and max_length > 2))
                    and getattr(self, "_fast_generate", True) and self.precision != "fp32" and self._select_kernels_fit(num_beams))
         if fast_ok:
             return self._generate_fast(encoder_outputs[0], attention_mask, batch_size, effective_batch_size, effective_batch_mult,
                                        num_beams, max_length, min_length, do_sample, early_stopping, temperature, top_k,
                                        pad_token_id, eos_token_id, length_penalty, num_return_sequences, decoder_start_token_id,
-                                       vocab_size)
+                                       vocab_size, top_p=top_p)
 
         if num_return_sequences > 1 or num_beams > 1:
             input_ids_len = input_ids.shape[-1]
@@ -229,7 +229,7 @@ class GenerationMixin:
     # ------------------------------------------------------------------ fast decode (same semantics, device-side loop)
     def _generate_fast(self, enc_hidden, attention_mask, batch_size, effective_batch_size, effective_batch_mult, num_beams,
                        max_length, min_length, do_sample, early_stopping, temperature, top_k, pad_token_id, eos_token_id,
-                       length_penalty, num_return_sequences, decoder_start_token_id, vocab_size):
+                       length_penalty, num_return_sequences, decoder_start_token_id, vocab_size, top_p=1.0):
         from kmbart.decode import get_session
         cfg = self.config
         eng = self._engine()
@@ -241,7 +241,7 @@ class GenerationMixin:
         sess.begin(enc_hidden, attention_mask, decoder_start_token_id, use_tbl=num_beams > 1)
         flb = self.final_logits_bias
         if num_beams == 1:
-            sel = dict(do_sample=bool(do_sample), temperature=float(temperature), top_k=int(top_k), eos=eos_token_id,
+            sel = dict(do_sample=bool(do_sample), temperature=float(temperature), top_k=int(top_k), top_p=float(top_p), eos=eos_token_id,
                        pad=pad_token_id, min_length=int(min_length))
             steps = max_length - 1
             for t in range(steps):

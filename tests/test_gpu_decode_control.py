@@ -121,14 +121,14 @@ def test_beam_step_kernel_matches_hf_loop_body(nb, early, lenpen):
     assert out.shape[0] == B and (out[:, 0] == 0).all()
 
 
-def _sample(lib, L, logits, temperature, top_k, seed, cur_len=3):
+def _sample(lib, L, logits, temperature, top_k, seed, cur_len=3, top_p=1.0):
     rows, V = logits.shape
     unfinished = torch.ones(rows, dtype=torch.int64, device="cuda")
     sent_len = torch.zeros(rows, dtype=torch.int64, device="cuda")
     out = torch.zeros(rows, 8, dtype=torch.int64, device="cuda")
     ids = torch.zeros(rows, dtype=torch.int64, device="cuda")
     sd = torch.tensor([seed], dtype=torch.int64, device="cuda")
-    L.check(lib.kmb_sample_select(logits.data_ptr(), V, rows, V, temperature, top_k, -1, 0, 0, cur_len, sd.data_ptr(), unfinished.data_ptr(),
+    L.check(lib.kmb_sample_select(logits.data_ptr(), V, rows, V, temperature, top_k, top_p, -1, 0, 0, cur_len, sd.data_ptr(), unfinished.data_ptr(),
                                   sent_len.data_ptr(), out.data_ptr(), 8, ids.data_ptr(), torch.cuda.current_stream().cuda_stream), "sample")
     torch.cuda.synchronize()
     assert torch.equal(out[:, cur_len], ids)
@@ -182,3 +182,38 @@ def test_sample_select_top_k_threshold_keeps_ties_and_ragged_rows():
     toks = _sample(lib, L, logits.cuda().contiguous(), 1.0, k, 4)
     kth = logits.topk(k, -1).values[:, -1]
     assert bool((logits.gather(1, toks.view(-1, 1)).squeeze(1) >= kth).all())
+
+
+def test_sample_select_nucleus_filter_matches_hf_rule():
+    """top_p: a token survives iff the probability mass sorted strictly before it is <= top_p (HF-3.0.2
+    top_k_top_p_filtering: cumulative softmax of the sorted logits, shifted right by one) — alone and after a top-k filter."""
+    L, lib = _lib()
+    V, rows = 2000, 2048
+    g = torch.Generator().manual_seed(17)
+    base = torch.randn(V, generator=g) * 2.0
+    logits = base.repeat(rows, 1).cuda().contiguous()
+
+    def hf_support(x, top_k, top_p, temperature=1.0):
+        x = x.clone() / temperature
+        if top_k > 0:
+            x[x < x.topk(top_k).values[-1]] = -float("inf")
+        sl, si = torch.sort(x, descending=True)
+        cum = torch.softmax(sl, -1).cumsum(-1)
+        rm = cum > top_p
+        rm[1:] = rm[:-1].clone()
+        rm[0] = False
+        keep = torch.zeros(V, dtype=torch.bool)
+        keep[si[~rm]] = True
+        return keep, torch.softmax(x.masked_fill(~keep, -float("inf")), -1)
+    for top_k, top_p, temp, seed in ((0, 0.8, 1.0, 1), (0, 0.3, 1.0, 2), (40, 0.9, 1.0, 3), (0, 0.8, 0.7, 4)):
+        keep, probs = hf_support(base, top_k, top_p, temp)
+        toks = _sample(lib, L, logits, temp, top_k, seed, top_p=top_p)
+        assert bool(keep[toks].all()), (top_k, top_p, "token outside the nucleus")
+        seen = torch.zeros(V, dtype=torch.bool)
+        seen[toks] = True
+        heavy = keep & (probs > 8.0 / rows)                  # every reasonably likely survivor shows up
+        assert bool(seen[heavy].all()), (top_k, top_p)
+        top = int(probs.argmax())
+        f = (toks == top).float().mean().item()
+        pt = probs[top].item()
+        assert abs(f - pt) <= 4.0 * (pt * (1 - pt) / rows) ** 0.5 + 1e-3, (top_k, top_p, f, pt)
