@@ -369,6 +369,32 @@ int kmb_adamw_multi(const void* table_dev, const void* chunk_map_dev, int n_chun
 int kmb_adamw_multi_part(const void* table_dev, const void* chunk_map_dev, int n_chunks, int* step_dev, double lr,
                          double beta1, double beta2, double eps, double weight_decay, int correct_bias,
                          const float* inv_scale_dev, int advance_step, kmb_stream_t stream);
+/* ---- data-parallel gradient exchange over NVLink peer memory (csrc/peer_exchange.cu).
+ * Replaces, on one NVSwitch node, the bucketed NCCL all-reduce that torch DDP performs for the reference
+ * (vcg_train.py:96-98, pretrain.py:96-98: DDP(model, find_unused_parameters=True)); kmbart/parallel.py falls back to
+ * NCCL when the ranks are not all peers of each other.
+ * kmb_ipc_export / kmb_ipc_open: CUDA IPC handle (64 bytes) of the allocation that contains `ptr`, plus the offset of
+ * `ptr` inside it; the opener maps the allocation and adds the offset itself. */
+int kmb_ipc_export(const void* ptr, unsigned char* handle64, unsigned long long* offset);
+int kmb_ipc_open(const unsigned char* handle64, void** base);
+int kmb_ipc_close(void* base);
+int kmb_peer_can_access(int dev, int peer_dev);   /* 1 / 0 */
+/* g: this rank's flat fp32 gradient buffer; staging: [2 lanes][world][slot_elems] fp32; flags: [2][n_regions][world] u32, zeroed;
+ * peer_*[r]: rank r's buffers mapped into this process (entry `rank` is ignored). */
+int kmb_peer_ctx_create(int rank, int world, float* g, void* const* peer_g, float* staging, void* const* peer_staging,
+                        unsigned* flags, void* const* peer_flags, size_t slot_elems, int n_regions, void** ctx_out);
+int kmb_peer_ctx_destroy(void* ctx);
+/* g[start, end) is final on `compute`: average it over the ranks on the exchange's own streams.  mode 0: copy engines
+ * + one small reduction kernel (no SM taken from a running sweep); mode 1: one kernel that loads the slice from every
+ * rank and stores the average to every rank (for regions exchanged after the sweep).  `value` is the same on every
+ * rank and grows with every exchange of this region; so must `mode` be. */
+int kmb_peer_exchange_region(void* ctx, int region, size_t start, size_t end, unsigned value, int mode, kmb_stream_t compute);
+/* orders `compute` after everything enqueued so far on the exchange's stream */
+int kmb_peer_join(void* ctx, kmb_stream_t compute);
+/* kmb_peer_mark remembers the current end of the exchange's streams; kmb_peer_join_mark orders `compute` after that
+ * point only (regions enqueued after the mark stay in flight: the optimizer joins them later, kmbart/optim.py) */
+int kmb_peer_mark(void* ctx);
+int kmb_peer_join_mark(void* ctx, kmb_stream_t compute);
 int kmb_cast_bf16(const float* src, void* dst, int64_t n, kmb_stream_t stream);
 int kmb_repack_img_weight(const float* w, void* w_feat_bf16, float* w_box, int d, int fin, kmb_stream_t stream);
 /* attention_mask (int64, 1 = keep) -> padding bytes (1 = pad): HF-3.0.2 invert_mask

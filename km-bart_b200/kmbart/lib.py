@@ -121,6 +121,17 @@ _PROTOS = {
                         c_void_p, c_void_p],
     "kmb_adamw_multi_part": [c_void_p, c_void_p, c_int, c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_int,
                              c_void_p, c_int, c_void_p],
+    "kmb_ipc_export": [c_void_p, c_void_p, C.POINTER(C.c_ulonglong)],
+    "kmb_ipc_open": [c_void_p, C.POINTER(c_void_p)],
+    "kmb_ipc_close": [c_void_p],
+    "kmb_peer_can_access": [c_int, c_int],
+    "kmb_peer_ctx_create": [c_int, c_int, c_void_p, C.POINTER(c_void_p), c_void_p, C.POINTER(c_void_p), c_void_p, C.POINTER(c_void_p),
+                            C.c_size_t, c_int, C.POINTER(c_void_p)],
+    "kmb_peer_ctx_destroy": [c_void_p],
+    "kmb_peer_exchange_region": [c_void_p, c_int, C.c_size_t, C.c_size_t, c_uint32, c_int, c_void_p],
+    "kmb_peer_join": [c_void_p, c_void_p],
+    "kmb_peer_mark": [c_void_p],
+    "kmb_peer_join_mark": [c_void_p, c_void_p],
     "kmb_cast_bf16": [c_void_p, c_void_p, c_int64, c_void_p],
     "kmb_repack_img_weight": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "kmb_invert_mask": [c_void_p, c_void_p, c_int64, c_void_p],

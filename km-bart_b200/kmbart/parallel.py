@@ -13,9 +13,120 @@ lives in one flat fp32 buffer and the backward is an ordered launch plan — to 
     NCCL runs it on its own stream over NVLink while the sweep continues; no bucket copies, no hooks;
   * `finish()` (last plan entry) joins the NCCL stream.
 
+  * on one NVSwitch node (every rank a CUDA peer of every other) the exchange itself is not NCCL but
+    csrc/peer_exchange.cu: copy-engine pushes between peer mappings of the flat gradient buffers plus one small
+    reduction kernel per region, on a private stream — no SM is taken from the backward sweep (PeerExchange below;
+    KMBART_GRAD_EXCHANGE=nccl forces the NCCL path).
+
 One process per GPU, launched by torchrun; works on any torch.distributed backend (tests use gloo on CPU)."""
+import ctypes as C
+import os
+import socket
+
 import torch
 import torch.distributed as dist
+
+PEER_PIECE = 12 * 1024 * 1024   # elements (48 MB): larger regions are exchanged in pieces
+_ipc_opened = {}     # handle bytes -> mapped base address (a process may map a peer allocation only once; never closed)
+
+
+class PeerExchange:
+    """Peer-memory gradient exchange for one flat gradient buffer (csrc/peer_exchange.cu).  `create` is collective:
+    every rank of `group` calls it; it returns None on every rank when any pair of ranks is not a CUDA peer on one
+    host (the caller then keeps NCCL)."""
+
+    @staticmethod
+    def create(G, regions, group=None):
+        from . import lib as L
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world < 2 or world > 8 or not G.is_cuda:
+            return None
+        lib = L.load()
+        dev = G.device.index if G.device.index is not None else torch.cuda.current_device()
+        chunk = max((((b - a + world - 1) // world) + 3) // 4 * 4 for a, b, _ in regions)
+        n_flags = 2 * len(regions) * world
+        flag_words = (n_flags + 63) // 64 * 64
+        # flags first (zeroed), then `world` staging slots; one allocation so one IPC mapping covers both
+        side = torch.zeros(flag_words + 2 * world * chunk, dtype=torch.float32, device=G.device)   # two lanes of slots
+        mine, ok = [], True
+        try:
+            for t in (G, side):
+                h = (C.c_ubyte * 64)()
+                off = C.c_ulonglong(0)
+                L.check(lib.kmb_ipc_export(t.data_ptr(), h, C.byref(off)), "kmb_ipc_export")
+                mine.append((bytes(h), int(off.value)))
+        except L.KmbartError:
+            ok = False
+        info = [None] * world
+        dist.all_gather_object(info, (socket.gethostname(), dev, ok, mine), group=group)
+        ok = all(i[2] for i in info) and len({i[0] for i in info}) == 1 and len({i[1] for i in info}) == world
+        ok = ok and all(lib.kmb_peer_can_access(dev, i[1]) for r, i in enumerate(info) if r != rank)
+        peer_g, peer_side = [0] * world, [0] * world
+        if ok:
+            try:
+                for r, i in enumerate(info):
+                    if r == rank:
+                        continue
+                    ptrs = []
+                    for hb, off in i[3]:
+                        base = _ipc_opened.get(hb)
+                        if base is None:
+                            out = C.c_void_p()
+                            L.check(lib.kmb_ipc_open(hb, C.byref(out)), "kmb_ipc_open")
+                            base = _ipc_opened[hb] = out.value
+                        ptrs.append(base + off)
+                    peer_g[r], peer_side[r] = ptrs
+            except L.KmbartError:
+                ok = False
+        flags = [None] * world
+        dist.all_gather_object(flags, ok, group=group)
+        if not all(flags):
+            return None
+        self = PeerExchange()
+        self.lib, self.L, self.side, self.G = lib, L, side, G
+        self.world, self.rank, self.regions = world, rank, list(regions)
+        arr = lambda v: (C.c_void_p * world)(*[x or None for x in v])
+        ctx = C.c_void_p()
+        L.check(lib.kmb_peer_ctx_create(rank, world, G.data_ptr(), arr(peer_g), side.data_ptr() + 4 * flag_words,
+                                        arr([p + 4 * flag_words if p else 0 for p in peer_side]), side.data_ptr(), arr(peer_side),
+                                        chunk, len(regions), C.byref(ctx)), "kmb_peer_ctx_create")
+        self.ctx = ctx
+        self.value = 0
+        tail = os.environ.get("KMBART_PEER_TAIL", "auto")      # ce | kernel | auto (kernel when world > 2)
+        self.kernel_tail = tail == "kernel" or (tail == "auto" and world > 2)
+        torch.cuda.synchronize(G.device)
+        dist.barrier(group=group)          # nobody signals before every rank has zeroed and mapped its flags
+        return self
+
+    def exchange(self, region_index, after_sweep=False):
+        """`after_sweep`: the region is exchanged when the backward sweep is over (same value on every rank) — with more
+        than two ranks it then goes through the one-kernel load/store path instead of the copy engines."""
+        a, b, _ = self.regions[region_index]
+        stream = torch.cuda.current_stream(self.G.device).cuda_stream
+        mode = 1 if (after_sweep and self.kernel_tail) else 0
+        self.L.check(self.lib.kmb_peer_exchange_region(self.ctx, region_index, a, b, self.value + 1, mode, stream), "kmb_peer_exchange_region")
+
+    def join(self):
+        stream = torch.cuda.current_stream(self.G.device).cuda_stream
+        self.L.check(self.lib.kmb_peer_join(self.ctx, stream), "kmb_peer_join")
+
+    def mark(self):
+        self.L.check(self.lib.kmb_peer_mark(self.ctx), "kmb_peer_mark")
+
+    def join_mark(self):
+        stream = torch.cuda.current_stream(self.G.device).cuda_stream
+        self.L.check(self.lib.kmb_peer_join_mark(self.ctx, stream), "kmb_peer_join_mark")
+
+    def end_step(self):
+        self.value += 1
+
+    def __del__(self):
+        ctx, self.ctx = getattr(self, "ctx", None), None
+        if ctx:
+            try:
+                self.lib.kmb_peer_ctx_destroy(ctx)
+            except Exception:
+                pass
 
 
 def layer_stage(name, n_dec, n_enc):
@@ -79,6 +190,26 @@ class FlatGradReducer:
         self.tail_ranges = [(a, b) for a, b, s_ in self.regions if s_ is None]   # element ranges of the flat buffers
         st.grad_reducer = self
         eng.grad_reducer = self
+        self.peer = None
+        self.deferred_stages = set()
+        self._marked = False
+        if self.world > 1 and st.G.is_cuda and os.environ.get("KMBART_GRAD_EXCHANGE", "peer") != "nccl":
+            # pieces of at most PEER_PIECE elements: consecutive pieces run on alternating lanes of the exchange, so the
+            # second half of one overlaps the first half of the next (matters for the 160 MB tied-embedding region)
+            pieces = []
+            for a, b, s_ in self.regions:
+                n = max(1, -(-(b - a) // PEER_PIECE))
+                step = (-(-(b - a) // n) + 63) // 64 * 64
+                pieces += [(lo, min(b, lo + step), s_) for lo in range(a, b, step)]
+            self.peer = PeerExchange.create(st.G, pieces, process_group)
+            if self.peer is not None:
+                self.regions = pieces
+                stages = sorted({s_ for _, _, s_ in pieces if s_ is not None})
+                if self.defer_tail:     # the last stage(s) of the sweep cannot finish their exchange before it ends either
+                    self.deferred_stages = set(stages[len(stages) - int(os.environ.get("KMBART_DEFER_STAGES", "1")):]) \
+                        if int(os.environ.get("KMBART_DEFER_STAGES", "1")) > 0 else set()
+                    self.tail_ranges = [(a, b) for a, b, s_ in pieces if s_ is None or s_ in self.deferred_stages]
+        self.transport = "peer" if self.peer is not None else ("nccl" if st.G.is_cuda else "gloo")
         eng.plans = {k: ({kk: vv for kk, vv in v.items() if not kk.startswith("bwd")} if isinstance(v, dict) else v)
                      for k, v in eng.plans.items()}   # backward plans are rebuilt with the reduction points
         if broadcast_parameters and self.world > 1:
@@ -91,9 +222,17 @@ class FlatGradReducer:
     def launch_stage(self, stage):
         if not self.enabled or self.world == 1:
             return 0
+        if os.environ.get("KMBART_GRAD_EXCHANGE") == "none":   # timing experiments: a data-parallel step with no exchange at all
+            return 0
         G = self.eng.store.G
-        for a, b, s in self.regions:
-            if s == stage:
+        for i, (a, b, s) in enumerate(self.regions):
+            if s == stage and self.peer is not None:
+                if stage in self.deferred_stages and not self._marked:
+                    self.peer.mark()             # finish() joins up to here; the optimizer joins the rest
+                    self._marked = True
+                self.peer.exchange(i, after_sweep=stage is None or stage in self.deferred_stages)
+                self.bytes_reduced += 4 * (b - a)
+            elif s == stage:
                 self.pending.append(dist.all_reduce(G[a:b], op=dist.ReduceOp.AVG if G.is_cuda else dist.ReduceOp.SUM,
                                                     group=self.group, async_op=True))
                 if not G.is_cuda:
@@ -102,6 +241,19 @@ class FlatGradReducer:
         return 0
 
     def finish(self):
+        if self.peer is not None and self.enabled and self.world > 1:
+            if self.defer_tail:
+                if not self._marked:
+                    self.peer.mark()
+                self._marked = False
+                self.peer.join_mark()            # everything but the deferred regions
+                self.launch_stage(None)
+                self.tail_pending = [self.peer]  # joined by AdamW.step() / wait_tail()
+            else:
+                self.launch_stage(None)
+                self.peer.join()
+            self.peer.end_step()
+            return 0
         n_before = len(self.pending)
         self.launch_stage(None)
         tail = self.pending[n_before:]
@@ -122,7 +274,10 @@ class FlatGradReducer:
     def wait_tail(self):
         """Orders the current stream after the deferred exchange of the last regions (no-op when nothing is pending)."""
         for w in self.tail_pending:
-            w.wait()
+            if w is self.peer:
+                w.join()
+            else:
+                w.wait()
         self.tail_pending = []
 
     class _NoSync:
