@@ -169,6 +169,14 @@ def bench_generation(model, cfg, dev, rank, world, dist, hbm_peak, peak_src):
     return out
 
 
+def _exchange_text(reducer):
+    if reducer.transport == "peer":
+        return ("FlatGradReducer over NVLink peer memory (csrc/peer_exchange.cu): per-layer regions averaged during the backward sweep by "
+                "copy-engine pushes + one small reduction kernel, the last regions (tied embedding, small tensors, encoder layer 0) "
+                + ("by one load/store kernel" if reducer.peer.kernel_tail else "the same way") + " while AdamW updates the others")
+    return ("FlatGradReducer: per-layer NCCL all-reduce (AVG) overlapped with backward, last region overlapped with the AdamW update of the others")
+
+
 def bench_workload(name, dev, rank, world, dist, steps, sustained, e2e=False):
     """One of the other BASELINE configs, device-resident inputs, fwd + bwd + AdamW, CUDA events, max over ranks."""
     import gc
@@ -326,7 +334,7 @@ def run_ours(args):
             step_model = DDP(model, device_ids=[local_rank], gradient_as_bucket_view=True)
         else:             # all-reduce points inside the backward launch plan, overlapped on NCCL's stream
             from kmbart.parallel import FlatGradReducer
-            FlatGradReducer(model, defer_tail=True)   # AdamW updates the finished regions while the last all-reduce is in flight
+            reducer = FlatGradReducer(model, defer_tail=True)   # AdamW updates the finished regions while the last exchange is in flight
     opt = AdamW(model.parameters(), lr=1e-5)
 
     dev_batch = make_batch(cfg, 1234 + rank, device=dev)
@@ -487,7 +495,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "configs[1]: KM-BART base VCG fine-tuning step, batch 128/GPU, 36 RoIx2052 + 64 ctx tokens "
                                "(S_e=100), 48 target tokens, dropout 0.1, AdamW lr 1e-5",
-                   "global_batch": B_PER_GPU * world, "parallelism": f"dp{world}", "grad_exchange": ("none" if world == 1 else ("torch DDP" if args.ddp else "FlatGradReducer: per-layer NCCL all-reduce (AVG) overlapped with backward, last region overlapped with the AdamW update of the others")),
+                   "global_batch": B_PER_GPU * world, "parallelism": f"dp{world}", "grad_exchange": ("none" if world == 1 else ("torch DDP" if args.ddp else _exchange_text(reducer))),
                    "l2": "per-step working set (~7 GB activations + 1.7 GB optimizer state) far exceeds the 126 MB L2",
                    "reference_script_path": ddp_leg},
         "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
