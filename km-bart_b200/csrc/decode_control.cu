@@ -51,6 +51,38 @@ __device__ __forceinline__ float dc_block_sum(float v, DcScratch& s) {
   return r;
 }
 
+// Row of logits -> shared memory (fp32), returns the thread's running maximum.  16-byte loads, four per thread in flight:
+// with one 4-byte load per thread per iteration the copy is latency bound (1024 x 4 B in flight per SM = 40 us for a
+// 50 k vocabulary, profiles/r02_decode_analysis.md); `f(i, v)` is applied to every element before it is stored.
+template <typename F>
+__device__ __forceinline__ float dc_stage_row(const float* __restrict__ x, float* xs, int V, F f) {
+  float mx = -INFINITY;
+  const int V4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? (V >> 2) : 0;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (int i = threadIdx.x; i < V4; i += 4 * DC_THREADS) {
+    float4 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * DC_THREADS < V4) a[u] = __ldg(x4 + i + u * DC_THREADS);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = i + u * DC_THREADS;
+      if (j < V4) {
+        float4 v = a[u];
+        v.x = f(4 * j, v.x); v.y = f(4 * j + 1, v.y); v.z = f(4 * j + 2, v.z); v.w = f(4 * j + 3, v.w);
+        reinterpret_cast<float4*>(xs)[j] = v;
+        mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+      }
+    }
+  }
+  for (int i = 4 * V4 + threadIdx.x; i < V; i += DC_THREADS) {
+    const float v = f(i, x[i]);
+    xs[i] = v;
+    mx = fmaxf(mx, v);
+  }
+  return mx;
+}
+
 // key of the k-th largest element of x[0, V) (1 <= k <= V)
 __device__ uint32_t dc_radix_kth(const float* x, int V, int k, DcScratch& s) {
   const int lane = threadIdx.x & 31;
@@ -138,8 +170,9 @@ __device__ uint32_t dc_radix_mass(const float* e, int V, float limit, DcScratch&
       float cum = above + incl - tot;
       const bool mine = cum <= limit && above + incl > limit;
       const unsigned who = __ballot_sync(0xffffffffu, mine);
+      const float all_bins = __shfl_sync(0xffffffffu, incl, 31);   // by every lane: a shuffle under `lane == 0` never returns
       if (who == 0) {                         // rounding: everything fits under the limit -> lowest populated bin
-        if (lane == 0) { s.bc[0] = 0; s.bc[2] = __float_as_uint(above + __shfl_sync(0xffffffffu, incl, 31)); }
+        if (lane == 0) { s.bc[0] = 0; s.bc[2] = __float_as_uint(above + all_bins); }
       } else if (lane == __ffs(who) - 1) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -157,6 +190,38 @@ __device__ uint32_t dc_radix_mass(const float* e, int V, float limit, DcScratch&
   return prefix;
 }
 
+// k-th largest key of a staged row for SMALL k (beam search: 2 * num_beams; top-k sampling: 50) without the four
+// histogram passes over the whole vocabulary: the k-th largest of the 1024 per-thread maxima is a lower bound t0 of the
+// answer (there are at least k elements >= t0), one pass collects the few elements >= t0, and the exact k-th largest is
+// selected among those.  Returns false (caller runs dc_radix_kth over the row) when k is large or the candidates overflow
+// (heavy ties, e.g. a forced-token step where all but one logit are -inf).
+constexpr int DC_CAND_CAP = 1024;
+struct DcCand {
+  float v[DC_CAND_CAP];
+  float tmax[DC_THREADS];
+  int n;
+};
+// `slack`: how many of the elements behind the thread maxima were removed from xs after the maxima were taken.
+__device__ bool dc_kth_filtered(const float* xs, int V, int k, int slack, float tmax, DcScratch& s, DcCand& cd, uint32_t* thr) {
+  if (k + slack > DC_THREADS / 8 || V < DC_THREADS) return false;
+  cd.tmax[threadIdx.x] = tmax;
+  if (threadIdx.x == 0) cd.n = 0;
+  __syncthreads();
+  const uint32_t t0 = dc_radix_kth(cd.tmax, DC_THREADS, k + slack, s);
+  for (int i = threadIdx.x; i < V; i += DC_THREADS) {
+    const float v = xs[i];
+    if (dc_key(v) >= t0) {
+      const int slot = atomicAdd(&cd.n, 1);
+      if (slot < DC_CAND_CAP) cd.v[slot] = v;
+    }
+  }
+  __syncthreads();
+  const int n = cd.n;
+  if (n > DC_CAND_CAP) return false;
+  *thr = dc_radix_kth(cd.v, n, k, s);
+  return true;
+}
+
 // ------------------------------------------------------------------ top-k / top-p sampling (num_beams == 1, do_sample)
 __global__ void __launch_bounds__(DC_THREADS) sample_select_kernel(const float* logits, int64_t ld, int V, float inv_temp, int top_k, float top_p, int eos, int pad,
                                                                   int ban_eos, int cur_len, const unsigned long long* seed, int64_t* unfinished,
@@ -166,19 +231,16 @@ __global__ void __launch_bounds__(DC_THREADS) sample_select_kernel(const float* 
   DcScratch& sc = *reinterpret_cast<DcScratch*>(dc_smem + (((size_t)V * 4 + 15) & ~(size_t)15));
   const int row = blockIdx.x;
   const float* x = logits + (int64_t)row * ld;
-  float mx = -INFINITY;
-  for (int i = threadIdx.x; i < V; i += DC_THREADS) {
-    float v = x[i];
-    if (ban_eos && i == eos) v = -INFINITY;
-    v *= inv_temp;
-    xs[i] = v;
-    mx = fmaxf(mx, v);
-  }
-  mx = dc_block_max(mx, sc);
+  __shared__ DcCand cd;
+  const float tmax = dc_stage_row(x, xs, V, [&](int i, float v) { return ((ban_eos && i == eos) ? -INFINITY : v) * inv_temp; });
+  const float mx = dc_block_max(tmax, sc);
   __syncthreads();
   // HF-3.0.2 top_k_top_p_filtering: top_k > 0 removes every logit below the k-th largest VALUE (ties survive); 0 = no filter
   uint32_t thr = 0;
-  if (top_k > 0 && top_k < V) thr = dc_radix_kth(xs, V, top_k, sc);
+  if (top_k > 0 && top_k < V && !dc_kth_filtered(xs, V, top_k, 0, tmax, sc, cd, &thr)) {
+    __syncthreads();
+    thr = dc_radix_kth(xs, V, top_k, sc);
+  }
   // probabilities in place, contiguous chunks per thread so that the scan below walks the vocabulary in index order
   const int chunk = (V + DC_THREADS - 1) / DC_THREADS;
   const int i0 = threadIdx.x * chunk, i1 = min(V, i0 + chunk);
@@ -269,22 +331,23 @@ __global__ void __launch_bounds__(DC_THREADS) beam_topk_kernel(const float* logi
   DcScratch& sc = *reinterpret_cast<DcScratch*>(dc_smem + (((size_t)V * 4 + 15) & ~(size_t)15));
   const int row = blockIdx.x;
   const float* x = logits + (int64_t)row * ld;
-  float mx = -INFINITY;
-  for (int i = threadIdx.x; i < V; i += DC_THREADS) {
-    float v = x[i];
-    if (force_tok >= 0 && i != force_tok) v = -INFINITY;
-    xs[i] = v;
-    mx = fmaxf(mx, v);
-  }
-  mx = dc_block_max(mx, sc);
+  __shared__ DcCand cd;
+  float tmax = dc_stage_row(x, xs, V, [&](int i, float v) { return (force_tok >= 0 && i != force_tok) ? -INFINITY : v; });
+  const float mx = dc_block_max(tmax, sc);
   float se = 0.f;
   for (int i = threadIdx.x; i < V; i += DC_THREADS) se += __expf(xs[i] - mx);
   se = dc_block_sum(se, sc);
   const float lse = logf(se);
   __syncthreads();
-  if (ban_eos && threadIdx.x == 0 && eos >= 0 && eos < V) xs[eos] = -INFINITY;
+  const bool banned = ban_eos && eos >= 0 && eos < V;
+  if (banned && threadIdx.x == 0) xs[eos] = -INFINITY;
   __syncthreads();
-  const uint32_t thr = dc_radix_kth(xs, V, K, sc);
+  // the thread maxima were taken before the ban (the log-sum-exp above includes the banned logit, like HF-3.0.2)
+  uint32_t thr = 0;
+  if (!dc_kth_filtered(xs, V, K, banned ? 1 : 0, tmax, sc, cd, &thr)) {
+    __syncthreads();
+    thr = dc_radix_kth(xs, V, K, sc);
+  }
   // strictly greater first (any order), then ties with the threshold in index order until K candidates are out
   if (threadIdx.x == 0) { sc.ibox[0] = 0; sc.ibox[1] = 0; }
   __syncthreads();
@@ -436,7 +499,7 @@ __global__ void __launch_bounds__(256) beam_update_kernel(const KmbBeamState st,
 
 }  // namespace kmb
 
-static const int DC_MAX_DYN_SMEM = 227 * 1024 - 1024;   // static shared memory of the kernels comes out of the same 227 KB
+static const int DC_MAX_DYN_SMEM = 227 * 1024 - 10 * 1024;   // static shared memory of the kernels comes out of the same 227 KB
 static int dc_row_smem(int V) { return (int)((((size_t)V * 4 + 15) & ~(size_t)15) + sizeof(kmb::DcScratch) + 64); }
 
 extern "C" int kmb_select_max_vocab(void) { return (DC_MAX_DYN_SMEM - (int)sizeof(kmb::DcScratch) - 128) / 4; }

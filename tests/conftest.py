@@ -12,3 +12,11 @@ for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (sm_100) GPU; run with -m gpu on the GPU box")
+
+
+def pytest_collection_modifyitems(config, items):
+    """A device-side hang must fail one test, not stall the whole GPU tier: every gpu test gets a thread-method timeout
+    (the signal method cannot interrupt a thread blocked inside the CUDA driver)."""
+    for item in items:
+        if item.get_closest_marker("gpu") is not None and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(900, method="thread"))

@@ -203,3 +203,27 @@ def test_sampling_without_top_k_filter_draws_from_the_whole_distribution(base):
     kth = lg.topk(50, -1).values[..., -1]
     chosen = lg.gather(-1, draws[0].cpu()[:, 1:].unsqueeze(-1)).squeeze(-1)
     assert bool((chosen < kth).any())
+
+
+@pytest.mark.timeout(300, method="thread")
+def test_nucleus_sampling_on_nearly_flat_logits_terminates_and_stays_in_the_nucleus(base):
+    """generate(do_sample=True, top_k=0, top_p=0.9) at the base shape: random-init logits are nearly flat, so the
+    nucleus holds tens of thousands of tokens and the mass radix descent reaches its "everything fits" branch — which
+    used to shuffle under a single-lane predicate and never return.  Every drawn token must lie inside the HF-3.0.2
+    nucleus of its own prefix (token kept iff the mass sorted strictly before it is <= top_p), with 2e-3 slack for bf16."""
+    ocfg, sd, batch = base
+    model = _model("MultiModalBartForConditionalGeneration", ocfg, sd, train=False)
+    gi = _gen_inputs(batch, 8)
+    with torch.no_grad():
+        torch.manual_seed(0)
+        t = model.generate(**gi, max_length=6, min_length=6, do_sample=True, top_k=0, top_p=0.9)
+    assert t.shape == (8, 6)
+    lg = _teacher_forced_logits(sd, ocfg, {k: v[:8] for k, v in batch.items()}, t)
+    p = torch.softmax(lg.float(), -1)
+    srt, _ = p.sort(-1, descending=True)
+    before = srt.cumsum(-1) - srt                                  # mass sorted strictly before each rank
+    chosen = p.gather(-1, t.cpu()[:, 1:].unsqueeze(-1)).squeeze(-1)
+    # mass strictly above the chosen token's probability
+    above = (p * (p > chosen.unsqueeze(-1))).sum(-1)
+    assert bool((above <= 0.9 + 2e-3).all()), above.max().item()
+    assert before.shape == p.shape
