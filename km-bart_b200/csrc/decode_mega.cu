@@ -180,15 +180,18 @@ __device__ void gemm_unit(const MgGemm& g, int u, int rows, const uint8_t* wslot
   const int n_strips = (g.N + 8 * NT - 1) / (8 * NT);
   const int strip = u % n_strips, kc = u / n_strips;
   const int n0 = strip * 8 * NT;
-  for (int m0 = 0; m0 < rows; m0 += 64) {
+  const bf16* abase = g.A + (int64_t)kc * C::KC + kg * KG + tg * 8;
+  uint4 alo[KB], ahi[KB];
+  auto load_a = [&](int m0) {
     const int ra = m0 + mt * 16 + gq, rb = ra + 8;
-    uint4 alo[KB], ahi[KB];
-    const bf16* abase = g.A + (int64_t)kc * C::KC + kg * KG + tg * 8;
 #pragma unroll
     for (int kb = 0; kb < KB; ++kb) {
       alo[kb] = ra < rows ? ldcg16(abase + (int64_t)ra * g.lda + kb * 32) : make_uint4(0, 0, 0, 0);
       ahi[kb] = rb < rows ? ldcg16(abase + (int64_t)rb * g.lda + kb * 32) : make_uint4(0, 0, 0, 0);
     }
+  };
+  load_a(0);
+  for (int m0 = 0; m0 < rows; m0 += 64) {
     float acc[NT][4];
 #pragma unroll
     for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
@@ -202,6 +205,9 @@ __device__ void gemm_unit(const MgGemm& g, int u, int rows, const uint8_t* wslot
         mma_bf16(acc[j], alo[kb].z, ahi[kb].z, alo[kb].w, ahi[kb].w, b.z, b.w);
       }
     }
+    // the next 64 rows of A travel from L2 while the partials are reduced and stored (rows > 64: beam search; with
+    // the loads at the top of the iteration every 64-row block paid one exposed L2 round trip)
+    if (m0 + 64 < rows) load_a(m0 + 64);
     // K-group partials -> scratch[kg][64][8NT], then every thread finishes a few (row, column-pair) outputs
     float* part = scratch + (size_t)kg * 64 * 8 * NT;
 #pragma unroll
