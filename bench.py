@@ -438,7 +438,11 @@ def run_ours(args):
         gemm_ms = tot / iters
         ach = 2.0 * M * N * K / (gemm_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_tc05_kernel<256,...,ES=4> encoder fc1 + bias + GELU + pre-activation copy, 12800x3072x768 (as launched in the step)",
-                "achieved": round(ach, 1), "peak": burst, "unit": "TFLOP/s", "frac": round(ach / burst, 4), "traffic": None,
+                "achieved": round(ach, 1), "peak": burst, "unit": "TFLOP/s", "frac": round(ach / burst, 4),
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full` launch
+                # (profiles/r01k_ncu_gemm_fc1_gelu_summary.txt: 31.29 + 110.39 MB; gemm_kernel.cuh unchanged since);
+                # algorithmic operand + output bytes are 181.6 MB, part of the output is still in L2 when the kernel ends
+                "traffic": 141675008, "traffic_source": "profiles/r01k_ncu_gemm_fc1_gelu_summary.txt",
                 "us_per_launch": round(gemm_ms * 1e3, 2),
                 "peak_source": peak_src + " burst (kernel timed alone, L2 flushed between launches)", "step_mfu": None}
         del A, W, out, pre, flush
