@@ -164,6 +164,17 @@ def plan_regions(names, offsets, numels, small_end, total, n_dec, n_enc):
     return [tuple(r) for r in regions]
 
 
+def split_pieces(regions, piece):
+    """Regions longer than `piece` elements cut into equal pieces (multiples of 64 elements, the last one takes the
+    remainder); order, coverage and stages are preserved."""
+    out = []
+    for a, b, s_ in regions:
+        n = max(1, -(-(b - a) // piece))
+        step = (-(-(b - a) // n) + 63) // 64 * 64
+        out += [(lo, min(b, lo + step), s_) for lo in range(a, b, step)]
+    return out
+
+
 class FlatGradReducer:
     def __init__(self, model, process_group=None, broadcast_parameters=True, engine=None, defer_tail=False):
         """`engine`: anything with `.store` (a kmbart.engine.ParamStore), `.cfg`, `.plans` — defaults to the model's
@@ -196,11 +207,7 @@ class FlatGradReducer:
         if self.world > 1 and st.G.is_cuda and os.environ.get("KMBART_GRAD_EXCHANGE", "peer") != "nccl":
             # pieces of at most PEER_PIECE elements: consecutive pieces run on alternating lanes of the exchange, so the
             # second half of one overlaps the first half of the next (matters for the 160 MB tied-embedding region)
-            pieces = []
-            for a, b, s_ in self.regions:
-                n = max(1, -(-(b - a) // PEER_PIECE))
-                step = (-(-(b - a) // n) + 63) // 64 * 64
-                pieces += [(lo, min(b, lo + step), s_) for lo in range(a, b, step)]
+            pieces = split_pieces(self.regions, PEER_PIECE)
             self.peer = PeerExchange.create(st.G, pieces, process_group)
             if self.peer is not None:
                 self.regions = pieces

@@ -357,8 +357,8 @@ class GenerationMixin:
     def _generate_beam_search(self, input_ids, cur_len, max_length, min_length, do_sample, early_stopping, temperature,
                               top_k, top_p, repetition_penalty, no_repeat_ngram_size, bad_words_ids, pad_token_id,
                               eos_token_id, batch_size, num_return_sequences, length_penalty, num_beams, vocab_size,
-                              encoder_outputs, attention_mask, use_cache, model_specific_kwargs, sess=None):
-        if (sess is None and not do_sample and repetition_penalty == 1.0 and no_repeat_ngram_size == 0 and bad_words_ids is None
+                              encoder_outputs, attention_mask, use_cache, model_specific_kwargs):
+        if (not do_sample and repetition_penalty == 1.0 and no_repeat_ngram_size == 0 and bad_words_ids is None
                 and max_length > 2 and cur_len == 1 and input_ids.is_cuda and getattr(self, "_device_controller", True)
                 and self._select_kernels_fit(num_beams)):
             return self._beam_search_device_controller(input_ids, max_length, min_length, early_stopping, pad_token_id, eos_token_id,
@@ -373,16 +373,12 @@ class GenerationMixin:
         past = (encoder_outputs, None) if encoder_outputs is not None else None
         done = [False for _ in range(batch_size)]
         while cur_len < max_length:
-            if sess is not None:   # fast decode chain: one graph launch, logits land in sess.logits
-                sess.step(cur_len - 1, self.final_logits_bias)
-                next_token_logits = sess.logits
-            else:
-                model_inputs = self.prepare_inputs_for_generation(input_ids, past=past, attention_mask=attention_mask,
-                                                                  use_cache=use_cache, **model_specific_kwargs)
-                outputs = self(**model_inputs)
-                next_token_logits = outputs[0][:, -1, :]
-                if self._use_cache(outputs, use_cache):
-                    past = outputs[1]
+            model_inputs = self.prepare_inputs_for_generation(input_ids, past=past, attention_mask=attention_mask,
+                                                              use_cache=use_cache, **model_specific_kwargs)
+            outputs = self(**model_inputs)
+            next_token_logits = outputs[0][:, -1, :]
+            if self._use_cache(outputs, use_cache):
+                past = outputs[1]
             if self.config.is_encoder_decoder and do_sample is False:
                 next_token_logits = self.adjust_logits_during_generation(next_token_logits, cur_len=cur_len,
                                                                          max_length=max_length)
@@ -442,10 +438,7 @@ class GenerationMixin:
             input_ids = input_ids[beam_idx, :]
             input_ids = torch.cat([input_ids, beam_tokens.unsqueeze(1)], dim=-1)
             cur_len = cur_len + 1
-            if sess is not None:
-                sess.reorder(beam_idx, cur_len - 2)
-                sess.ids.copy_(beam_tokens)
-            elif past is not None:
+            if past is not None:
                 past = self._reorder_cache(past, beam_idx)
 
         for batch_idx in range(batch_size):

@@ -115,3 +115,26 @@ def test_region_plan_is_contiguous_and_ordered():
     finally:
         P.layer_stage = orig
     assert regs == [(0, 10, None), (10, 164, 1), (164, 292, 0), (292, 384, None)]
+
+
+def test_exchange_pieces_cover_every_region_once():
+    """kmbart.parallel.split_pieces: the pieces of the peer-memory exchange partition each region, keep its stage and
+    order, start on 64-element boundaries relative to the region start, and never exceed the piece size by more than the
+    64-element rounding."""
+    from kmbart.parallel import split_pieces
+    regions = [(0, 10, None), (10, 7_100_010, 3), (7_100_010, 7_100_011, 2), (7_100_011, 50_000_000, None)]
+    piece = 12 * 1024 * 1024
+    out = split_pieces(regions, piece)
+    pos, ri = 0, 0
+    for a, b, s_ in out:
+        assert a == pos and b > a
+        while not (regions[ri][0] <= a and b <= regions[ri][1]):
+            ri += 1
+        assert s_ == regions[ri][2]
+        assert (a - regions[ri][0]) % 64 == 0
+        assert b - a <= piece + 64
+        pos = b
+    assert pos == regions[-1][1]
+    assert [r for r in out if r[2] == 3] == [(10, 7_100_010, 3)]                  # below the piece size: untouched
+    assert len([r for r in out if r[0] >= 7_100_011]) == 4                        # 42.9 M elements -> 4 pieces
+    assert split_pieces([(0, 5, 1)], 2) == [(0, 5, 1)]                            # rounding to 64 never produces empty pieces
