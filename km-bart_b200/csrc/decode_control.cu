@@ -342,7 +342,63 @@ __global__ void __launch_bounds__(DC_THREADS) beam_topk_kernel(const float* logi
   const bool banned = ban_eos && eos >= 0 && eos < V;
   if (banned && threadIdx.x == 0) xs[eos] = -INFINITY;
   __syncthreads();
-  // the thread maxima were taken before the ban (the log-sum-exp above includes the banned logit, like HF-3.0.2)
+  // Fast path for K + 1 <= 32 (beam search at the reference's num_beams = 5 needs K = 10): the (K + slack)-th largest of
+  // the 32 WARP maxima bounds the K-th largest logit from below, one pass collects the ~K..2K logits above the bound
+  // with their indices, and each collected logit finds its rank by counting — no histogram passes, no second scan of the
+  // row for the output.  The maxima were taken before the ban, hence slack = 1 (the log-sum-exp above includes the banned
+  // logit, like HF-3.0.2).  Heavy ties (forced-token steps) overflow the list and take the general path below.
+  {
+    __shared__ int cidx[DC_CAND_CAP];
+    __shared__ float wmax[DC_WARPS];
+    __shared__ uint32_t t0s;
+    const int lane_ = threadIdx.x & 31, wid_ = threadIdx.x >> 5;
+    const int kk = K + (banned ? 1 : 0);
+    const float wm = warp_max(tmax);
+    if (lane_ == 0) wmax[wid_] = wm;
+    if (threadIdx.x == 0) cd.n = 0;
+    __syncthreads();
+    if (kk <= DC_WARPS && V >= DC_THREADS) {
+      if (wid_ == 0) {
+        const float mine = wmax[lane_];
+        int r = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float o = __shfl_sync(0xffffffffu, mine, j);
+          r += (o > mine) || (o == mine && j < lane_);
+        }
+        if (r == kk - 1) t0s = dc_key(mine);
+      }
+      __syncthreads();
+      const uint32_t t0 = t0s;
+      for (int i = threadIdx.x; i < V; i += DC_THREADS) {
+        const float v = xs[i];
+        if (dc_key(v) >= t0) {
+          const int slot = atomicAdd(&cd.n, 1);
+          if (slot < DC_CAND_CAP) { cd.v[slot] = v; cidx[slot] = i; }
+        }
+      }
+      __syncthreads();
+      const int n = cd.n;
+      if (n <= DC_CAND_CAP) {                     // n >= K by construction
+        const float bsc_ = beam_scores[row];
+        for (int c = threadIdx.x; c < n; c += DC_THREADS) {
+          const float v = cd.v[c];
+          const int i = cidx[c];
+          int r = 0;
+          for (int j = 0; j < n; ++j) {
+            const float o = cd.v[j];
+            r += (o > v) || (o == v && cidx[j] < i);
+          }
+          if (r < K) {
+            cand_val[(int64_t)row * K + r] = ((v - mx) - lse) + bsc_;
+            cand_tok[(int64_t)row * K + r] = i;
+          }
+        }
+        return;
+      }
+      __syncthreads();
+    }
+  }
   uint32_t thr = 0;
   if (!dc_kth_filtered(xs, V, K, banned ? 1 : 0, tmax, sc, cd, &thr)) {
     __syncthreads();
@@ -499,7 +555,7 @@ __global__ void __launch_bounds__(256) beam_update_kernel(const KmbBeamState st,
 
 }  // namespace kmb
 
-static const int DC_MAX_DYN_SMEM = 227 * 1024 - 10 * 1024;   // static shared memory of the kernels comes out of the same 227 KB
+static const int DC_MAX_DYN_SMEM = 227 * 1024 - 14 * 1024;   // static shared memory of the kernels comes out of the same 227 KB
 static int dc_row_smem(int V) { return (int)((((size_t)V * 4 + 15) & ~(size_t)15) + sizeof(kmb::DcScratch) + 64); }
 
 extern "C" int kmb_select_max_vocab(void) { return (DC_MAX_DYN_SMEM - (int)sizeof(kmb::DcScratch) - 128) / 4; }
