@@ -439,10 +439,11 @@ def run_ours(args):
         ach = 2.0 * M * N * K / (gemm_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_tc05_kernel<256,...,ES=4> encoder fc1 + bias + GELU + pre-activation copy, 12800x3072x768 (as launched in the step)",
                 "achieved": round(ach, 1), "peak": burst, "unit": "TFLOP/s", "frac": round(ach / burst, 4),
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full` launch
-                # (profiles/r01k_ncu_gemm_fc1_gelu_summary.txt: 31.29 + 110.39 MB; gemm_kernel.cuh unchanged since);
-                # algorithmic operand + output bytes are 181.6 MB, part of the output is still in L2 when the kernel ends
-                "traffic": 141675008, "traffic_source": "profiles/r01k_ncu_gemm_fc1_gelu_summary.txt",
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch of exactly these launches inside a training step
+                # (ncu over tests/prof_step.py, mean of the 6 encoder fc1 launches: 30.6 MB read + 107.1 MB written;
+                # profiles/r02_final_gemm_dram_traffic_per_launch.csv, IDs 3..23); algorithmic operand + output bytes are
+                # 181.6 MB, part of the output is still in L2 when the kernel ends
+                "traffic": 137645141, "traffic_source": "profiles/r02_final_gemm_dram_traffic_per_launch.csv",
                 "us_per_launch": round(gemm_ms * 1e3, 2),
                 "peak_source": peak_src + " burst (kernel timed alone, L2 flushed between launches)", "step_mfu": None}
         del A, W, out, pre, flush
