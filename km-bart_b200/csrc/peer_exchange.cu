@@ -16,10 +16,14 @@
 //   5. signal DONE[region][me] on every peer, wait for DONE[region][p] from every peer
 //
 // Every rank ends with bit-identical averaged gradients.  Flags are step counters (monotonic, never reset) in a
-// peer-mapped array; the waits are one-warp kernels polling LOCAL memory (the signaller writes across NVLink), with a
-// 20 s watchdog that traps instead of hanging the device.  All of it runs on private non-blocking streams — two lanes
-// (regions alternate between them, each lane has its own staging slots) so that step 4 of one region overlaps step 1
-// of the next; the compute stream only records "region ready" events and joins at the end of the sweep.
+// peer-mapped array, written and awaited by stream memory operations (cuStreamBatchMemOp: the front end executes them, no
+// CTA has to find a slot beside the compute stream's grids); KMBART_PEER_SIGNAL=kernel selects one-warp kernels instead
+// (the waiter polls LOCAL memory, the signaller writes across NVLink; 20 s watchdog that traps instead of hanging).
+// All of it runs on private, highest-priority, non-blocking streams — two lanes (regions alternate between them, each
+// lane has its own staging slots) so that step 4 of one region overlaps step 1 of the next; the compute stream only
+// records "region ready" events and joins at the end of the sweep.  Regions that are exchanged after the sweep use,
+// at more than two ranks, one kernel that loads the slice from every rank and stores the average to every rank
+// (px_twoshot_kernel): `world - 1` copy-engine transfers per phase are executed one at a time and lose to NVLink there.
 #include <cuda.h>
 #include <string.h>
 #include "common.cuh"

@@ -9,16 +9,17 @@ lives in one flat fp32 buffer and the backward is an ordered launch plan — to 
   * the flat buffer is cut into contiguous regions by the point of the backward sweep at which they are complete
     (decoder layer L-1 ... 0, encoder layer L-1 ... 0, then "the rest": small tensors, image projection,
     positions and the tied embedding, whose gradient is only final after the encoder embedding backward);
-  * the plan launches `all_reduce(region, AVG, async_op=True)` right after the kernel that completes a region —
-    NCCL runs it on its own stream over NVLink while the sweep continues; no bucket copies, no hooks;
-  * `finish()` (last plan entry) joins the NCCL stream.
+  * the plan starts the exchange of a region right after the kernel that completes it, on streams of its own,
+    while the sweep continues; no bucket copies, no hooks;
+  * `finish()` (last plan entry) joins; with `defer_tail=True` the regions that cannot finish before the sweep ends
+    stay in flight and `kmbart.optim.AdamW.step()` joins them after it has updated everything else.
 
-  * on one NVSwitch node (every rank a CUDA peer of every other) the exchange itself is not NCCL but
-    csrc/peer_exchange.cu: copy-engine pushes between peer mappings of the flat gradient buffers plus one small
-    reduction kernel per region, on a private stream — no SM is taken from the backward sweep (PeerExchange below;
-    KMBART_GRAD_EXCHANGE=nccl forces the NCCL path).
+Transport: on one NVSwitch node (every rank a CUDA peer of every other) `PeerExchange` — csrc/peer_exchange.cu,
+copy-engine pushes between CUDA-IPC mappings of the ranks' gradient buffers plus one small reduction kernel per
+region, flags by stream memory operations: no SM is taken from the backward sweep (profiles/r02_dp_timeline.md).
+Otherwise (or with KMBART_GRAD_EXCHANGE=nccl) `all_reduce(region, AVG, async_op=True)` per region; gloo on CPU (tests).
 
-One process per GPU, launched by torchrun; works on any torch.distributed backend (tests use gloo on CPU)."""
+One process per GPU, launched by torchrun."""
 import ctypes as C
 import os
 import socket
