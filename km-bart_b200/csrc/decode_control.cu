@@ -331,8 +331,31 @@ __global__ void __launch_bounds__(DC_THREADS) beam_topk_kernel(const float* logi
   DcScratch& sc = *reinterpret_cast<DcScratch*>(dc_smem + (((size_t)V * 4 + 15) & ~(size_t)15));
   const int row = blockIdx.x;
   const float* x = logits + (int64_t)row * ld;
+  if (force_tok >= 0 && force_tok < V) {
+    // Forced step (HF-3.0.2 adjust_logits_during_generation: BOS at the first step, EOS at max_length - 1): every other
+    // logit is -inf, so log_softmax gives the forced token 0 (when its logit is finite) and -inf elsewhere; the K best are the
+    // forced token followed by the lowest token indices (ties at -inf in index order).  No pass over the vocabulary.
+    if (threadIdx.x == 0) {
+      const float xf = x[force_tok];
+      const bool dead = (ban_eos && force_tok == eos) || !(xf > -INFINITY && xf < INFINITY);
+      const float bsc = beam_scores[row];
+      int out = 0;
+      if (!dead) {
+        cand_val[(int64_t)row * K] = ((xf - xf) - 0.f) + bsc;
+        cand_tok[(int64_t)row * K] = force_tok;
+        out = 1;
+      }
+      for (int i = 0; out < K && i < V; ++i) {
+        if (!dead && i == force_tok) continue;
+        cand_val[(int64_t)row * K + out] = -INFINITY;
+        cand_tok[(int64_t)row * K + out] = i;
+        ++out;
+      }
+    }
+    return;
+  }
   __shared__ DcCand cd;
-  float tmax = dc_stage_row(x, xs, V, [&](int i, float v) { return (force_tok >= 0 && i != force_tok) ? -INFINITY : v; });
+  float tmax = dc_stage_row(x, xs, V, [&](int i, float v) { return v; });
   const float mx = dc_block_max(tmax, sc);
   float se = 0.f;
   for (int i = threadIdx.x; i < V; i += DC_THREADS) se += __expf(xs[i] - mx);
