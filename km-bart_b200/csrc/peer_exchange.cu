@@ -430,9 +430,23 @@ extern "C" int kmb_peer_exchange_region(void* ctx, int region, size_t start, siz
       size_t n = (lo_ + chunk <= len ? chunk : len - lo_);
       PxBufs bufs;
       for (int r = 0; r < PX_MAX_WORLD; ++r) bufs.p[r] = r == me ? c->g + start : (r < W ? c->peer_g[r] + start : nullptr);
+      // One CTA per SM: 256 threads x 2 x 16 B x `world` loads in flight per SM is far more than NVLink needs, and every
+      // further resident CTA (94 registers x 256 threads) takes occupancy from the AdamW kernel that runs beside it
+      // (4 GPUs, ms per step: cap 592 12.53, 296 12.51, 148 12.45).  KMBART_PEER_TWOSHOT_CTAS overrides (A/B timing).
+      static int cap = 0;
+      if (!cap) {
+        const char* e = getenv("KMBART_PEER_TWOSHOT_CTAS");
+        cap = e ? atoi(e) : 0;
+        if (cap < 1) {
+          int dev = 0, sms = 0;
+          cudaGetDevice(&dev);
+          cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+          cap = sms > 0 ? sms : 148;
+        }
+      }
       int blocks = (int)((n / 8 + 255) / 256);
       if (blocks < 1) blocks = 1;
-      if (blocks > 592) blocks = 592;
+      if (blocks > cap) blocks = cap;
       px_twoshot_kernel<<<blocks, 256, 0, comm>>>(bufs, lo_, n, W, 1.0f / (float)W);
     }
     px_signal(c, comm, f_fin + me, value);
