@@ -255,53 +255,76 @@ __global__ void __launch_bounds__(DC_THREADS) sample_select_kernel(const float* 
     if (keep) last_kept = i;
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (top_p < 1.0f) {
-    // nucleus filter on the surviving probabilities (HF applies it after the top-k filter, on the renormalised softmax)
-    const float tot0 = dc_block_sum(loc, sc);
+  // Inverse-CDF draw over the surviving probabilities in index order (exclusive scan of the per-thread chunk sums, fixed
+  // order).  Nucleus (top_p < 1, HF-3.0.2 top_k_top_p_filtering after the top-k filter: a token survives iff the mass of
+  // the strictly more probable tokens is <= top_p): sampling from the renormalised nucleus is sampling from the whole
+  // distribution conditioned on landing inside it, so the kernel draws, measures the mass above the drawn token with one
+  // pass, and redraws (next counter value) when it fell outside — acceptance probability >= top_p, no sort and no
+  // histogram.  After DC_NUCLEUS_TRIES rejections the exact threshold (dc_radix_mass) filters the row and one more draw decides.
+  constexpr int DC_NUCLEUS_TRIES = 24;
+  const bool nucleus = top_p < 1.0f;
+  for (int attempt = 0;; ++attempt) {
+    const bool exact = nucleus && attempt == DC_NUCLEUS_TRIES;
+    if (exact) {
+      const float tot0 = dc_block_sum(loc, sc);
+      __syncthreads();
+      const uint32_t pthr = dc_radix_mass(xs, V, top_p * tot0, sc);
+      loc = 0.f;
+      last_kept = -1;
+      for (int i = i0; i < i1; ++i) {
+        const float e = xs[i];
+        const bool keep = e > 0.f && __float_as_uint(e) >= pthr;
+        if (!keep) xs[i] = 0.f;
+        else { loc += e; last_kept = i; }
+      }
+    }
+    float incl = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
     __syncthreads();
-    const uint32_t pthr = dc_radix_mass(xs, V, top_p * tot0, sc);
-    loc = 0.f;
-    last_kept = -1;
+    if (lane == 31) sc.red[wid] = incl;
+    if (threadIdx.x == 0) { sc.ibox[0] = -1; sc.ibox[2] = 0; }
+    __syncthreads();
+    float wbase = 0.f, total = 0.f;
+    for (int w = 0; w < DC_WARPS; ++w) {
+      const float t = sc.red[w];
+      if (w < wid) wbase += t;
+      total += t;
+    }
+    atomicMax(&sc.ibox[0], last_kept);   // fallback: the last surviving token (rounding can push the target past the total)
+    const float excl = wbase + incl - loc;
+    // one uniform draw per (seed, row, step, attempt)
+    const unsigned long long bits = mix64(seed[0] ^ mix64(((unsigned long long)row << 20) + (unsigned long long)cur_len + 0x9E3779B97F4A7C15ULL +
+                                                          (unsigned long long)attempt * 0xD1B54A32D192ED03ULL));
+    const float u = (float)(bits >> 40) * (1.0f / 16777216.0f);
+    const float target = u * total;
+    __syncthreads();
+    if (loc > 0.f && excl <= target && target < excl + loc) {
+      float run = excl;
+      int pick = last_kept;
+      for (int i = i0; i < i1; ++i) {
+        run += xs[i];
+        if (xs[i] > 0.f && target < run) { pick = i; break; }
+      }
+      sc.ibox[1] = pick;
+      sc.ibox[2] = 1;
+    }
+    __syncthreads();
+    if (!nucleus || exact) break;
+    // mass of the tokens strictly more probable than the drawn one
+    const int tokc = (sc.ibox[2] == 1) ? sc.ibox[1] : sc.ibox[0];
+    const float ep = tokc >= 0 ? xs[tokc] : 0.f;
+    float above = 0.f;
     for (int i = i0; i < i1; ++i) {
       const float e = xs[i];
-      const bool keep = e > 0.f && __float_as_uint(e) >= pthr;
-      if (!keep) xs[i] = 0.f;
-      else { loc += e; last_kept = i; }
+      above += e > ep ? e : 0.f;
     }
-  }
-  // exclusive scan of the chunk sums over the 1024 threads (fixed order)
-  float incl = loc;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const float t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  __syncthreads();
-  if (lane == 31) sc.red[wid] = incl;
-  if (threadIdx.x == 0) { sc.ibox[0] = -1; sc.ibox[2] = 0; }
-  __syncthreads();
-  float wbase = 0.f, total = 0.f;
-  for (int w = 0; w < DC_WARPS; ++w) {
-    const float t = sc.red[w];
-    if (w < wid) wbase += t;
-    total += t;
-  }
-  atomicMax(&sc.ibox[0], last_kept);   // fallback: the last surviving token (rounding can push the target past the total)
-  const float excl = wbase + incl - loc;
-  // one uniform draw per (seed, row, step)
-  const unsigned long long bits = mix64(seed[0] ^ mix64(((unsigned long long)row << 20) + (unsigned long long)cur_len + 0x9E3779B97F4A7C15ULL));
-  const float u = (float)(bits >> 40) * (1.0f / 16777216.0f);
-  const float target = u * total;
-  __syncthreads();
-  if (loc > 0.f && excl <= target && target < excl + loc) {
-    float run = excl;
-    int pick = last_kept;
-    for (int i = i0; i < i1; ++i) {
-      run += xs[i];
-      if (xs[i] > 0.f && target < run) { pick = i; break; }
-    }
-    sc.ibox[1] = pick;
-    sc.ibox[2] = 1;
+    above = dc_block_sum(above, sc);
+    if (above <= top_p * total) break;       // block-uniform: inside the nucleus
+    __syncthreads();
   }
   __syncthreads();
   if (threadIdx.x == 0) {
